@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's R interface for the gene-set scoring hot path.
+
+Same function names, argument meaning, defaults and error behaviour as the exported R
+functions (reference `R/plaid.R`, `NAMESPACE:3-16`), so the parity tests read like tests of
+the R package:
+
+    plaid(X, matG, stats="mean", chunk=None, normalize=True)        R/plaid.R:60-87
+    chunked_crossprod(x, y, chunk=None)                              R/plaid.R:100-123
+    normalize_medians(x, ignore_zero=None)                           R/plaid.R:554-575
+    colranks(X, sparse=None, signed=False, keep_zero=False, ties_method="average")  :589-623
+    sparse_colranks(X, signed=False, ties_method="average")          R/plaid.R:631-650
+    replaid_scse / replaid_sing / replaid_ssgsea / replaid_ucell / replaid_aucell   :155-309
+
+Everything numeric happens in libplaidgpu.so (hand-written sm_100a CUDA) through the C ABI
+of include/plaidgpu.h.  What stays on the host is exactly what stays in R in the drop-in
+package (rpkg/R/plaid.R): matching rows by NAME (intersect/match) and dimnames.  There is
+no CPU fallback: without the library or without a B200 these functions raise.
+
+Matrices: `NamedMatrix(mat, rownames, colnames)`; `mat` is a scipy.sparse matrix (R
+dgCMatrix), a 2-D numpy array (R base matrix) or a `DeviceCSC` / CUDA torch tensor for
+device-resident pipelines.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # scipy is only needed to recognise / build sparse inputs
+    import scipy.sparse as sp
+except Exception:  # pragma: no cover
+    sp = None
+
+
+@dataclass
+class NamedMatrix:
+    mat: object
+    rownames: Optional[Sequence[str]] = None
+    colnames: Optional[Sequence[str]] = None
+
+    @property
+    def shape(self):
+        return tuple(self.mat.shape)
+
+
+@dataclass
+class DeviceCSC:
+    """A dgCMatrix whose slots are CUDA torch tensors (p int32[N+1], i int32[nnz], x float64[nnz])."""
+    p: object
+    i: object
+    x: object
+    shape: tuple
+
+    @property
+    def nnz(self):
+        return int(self.x.numel())
+
+
+def _message(msg: str):  # R message(): stderr
+    print(msg, file=sys.stderr)
+
+
+# ---------------------------------------------------------------------------------------
+# context handling
+# ---------------------------------------------------------------------------------------
+class Context:
+    """One libplaidgpu context = one GPU (`plaidgpu_init`)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.plaidgpu_init(int(device), C.byref(h))
+        if rc != L.OK:
+            raise L.PlaidGpuError(rc, f"plaidgpu_init(device={device}) failed: no usable sm_100 GPU "
+                                      "(plaid_b200 has no CPU fallback)")
+        self.h = h
+        self.device = device
+        self._keep = []  # host arrays that must outlive a call
+        self._gkey = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.plaidgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != L.OK:
+            raise L.PlaidGpuError(rc, (self.lib.plaidgpu_last_error(self.h) or b"").decode())
+
+    # -- gene sets -------------------------------------------------------------------------
+    def set_genesets(self, G):
+        """Register matG (genes x sets, scipy sparse).  Values only matter as zero / non-zero."""
+        G = sp.csc_matrix(G)
+        G.sort_indices()
+        key = (G.shape, G.nnz, hash(G.indptr.tobytes()), hash(G.indices.tobytes()), hash(G.data.tobytes()))
+        if key == self._gkey:
+            return
+        gp = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        gi = np.ascontiguousarray(G.indices, dtype=np.int32)
+        gx = np.ascontiguousarray(G.data, dtype=np.float64)
+        self.check(self.lib.plaidgpu_set_genesets(self.h, G.shape[0], G.shape[1], gp.ctypes.data,
+                                                  gi.ctypes.data, gx.ctypes.data))
+        self._gkey = key
+
+    def launch_count(self) -> int:
+        return int(self.lib.plaidgpu_launch_count(self.h))
+
+    def kernel_ms(self, which: int) -> float:
+        return float(self.lib.plaidgpu_last_kernel_ms(self.h, which))
+
+    def plan_info(self) -> dict:
+        ts, nt, wp, ct = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        nm = C.c_int64()
+        self.check(self.lib.plaidgpu_plan_info(self.h, C.byref(ts), C.byref(nt), C.byref(nm), C.byref(wp), C.byref(ct)))
+        return {"tile_sets": ts.value, "n_tiles": nt.value, "nnz_mapped": nm.value,
+                "warps_per_cta": wp.value, "ctas": ct.value}
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---------------------------------------------------------------------------------------
+# marshalling
+# ---------------------------------------------------------------------------------------
+def _is_torch(t) -> bool:
+    return type(t).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _matrix_struct(m, keep: list) -> L.Matrix:
+    """Describe X for the C ABI.  `keep` receives the arrays that back the pointers."""
+    M = L.Matrix()
+    if isinstance(m, DeviceCSC):
+        M.kind, M.location = L.CSC, L.DEVICE
+        M.P, M.N = int(m.shape[0]), int(m.shape[1])
+        M.p, M.i, M.x = m.p.data_ptr(), m.i.data_ptr(), m.x.data_ptr()
+        keep.append(m)
+        return M
+    if _is_torch(m):
+        if m.dim() != 2:
+            raise ValueError("dense device X must be 2-D")
+        # R layout is column-major: a torch tensor of shape (N, P) contiguous == P x N column-major
+        raise TypeError("pass dense device matrices as DeviceDense(t_colmajor, shape)")
+    if isinstance(m, DeviceDense):
+        M.kind, M.location = L.DENSE, L.DEVICE
+        M.P, M.N = int(m.shape[0]), int(m.shape[1])
+        M.x = m.x.data_ptr()
+        keep.append(m)
+        return M
+    if sp is not None and sp.issparse(m):
+        m = sp.csc_matrix(m)
+        m.sort_indices()
+        p = np.ascontiguousarray(m.indptr, dtype=np.int32)
+        i = np.ascontiguousarray(m.indices, dtype=np.int32)
+        x = np.ascontiguousarray(m.data, dtype=np.float64)
+        keep += [p, i, x]
+        M.kind, M.location = L.CSC, L.HOST
+        M.P, M.N = int(m.shape[0]), int(m.shape[1])
+        M.p, M.i, M.x = p.ctypes.data, i.ctypes.data, x.ctypes.data
+        return M
+    a = np.asarray(m, dtype=np.float64)
+    if a.ndim == 1:  # a bare vector is one sample (R/plaid.R:63)
+        a = a[:, None]
+    a = np.asfortranarray(a)
+    keep.append(a)
+    M.kind, M.location = L.DENSE, L.HOST
+    M.P, M.N = int(a.shape[0]), int(a.shape[1])
+    M.x = a.ctypes.data
+    return M
+
+
+@dataclass
+class DeviceDense:
+    """Column-major P x N float64 matrix in device memory (a 1-D or (N, P)-contiguous CUDA tensor)."""
+    x: object
+    shape: tuple
+
+
+def make_rowmap(x_rownames: Sequence[str], g_rownames: Sequence[str]) -> np.ndarray:
+    """rowmap[r] = row of matG aligned with X row r, or -1: `intersect(rownames(X), rownames(matG))`
+    + `X[gg,]` / `matG[gg,]` (R/plaid.R:65-72) — first occurrence of a duplicated name wins."""
+    gpos = {}
+    for k, n in enumerate(g_rownames):
+        gpos.setdefault(n, k)
+    out = np.full(len(x_rownames), -1, dtype=np.int32)
+    seen = set()
+    for r, n in enumerate(x_rownames):
+        if n in seen:
+            continue
+        seen.add(n)
+        k = gpos.get(n)
+        if k is not None:
+            out[r] = k
+    return out
+
+
+def _opts(lib, **kw) -> L.Opts:
+    o = L.Opts()
+    lib.plaidgpu_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _score(X: NamedMatrix, matG: NamedMatrix, opts_kw: dict, ctx: Optional[Context], out=None):
+    ctx = ctx or default_context()
+    Xm = X.mat
+    xr = X.rownames
+    if xr is None or matG.rownames is None:
+        _message("[plaid] ERROR. No overlapping features.")  # NULL rownames: intersect() is empty
+        return None
+    rowmap = make_rowmap(xr, matG.rownames)
+    if not (rowmap >= 0).any():  # R/plaid.R:66-69
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    ctx.set_genesets(matG.mat)
+    keep: list = []
+    M = _matrix_struct(Xm, keep)
+    if M.P != len(xr):
+        raise ValueError("rownames(X) does not match nrow(X)")
+    S = int(matG.mat.shape[1])
+    if out is None:
+        res = np.empty((S, M.N), dtype=np.float64, order="F")
+        out_loc, out_ptr = L.HOST, res.ctypes.data
+    else:  # caller-provided buffer: numpy F-order or CUDA tensor holding S x N column-major
+        res = out
+        out_loc = L.DEVICE if (_is_torch(out) and out.is_cuda) else L.HOST
+        out_ptr = _ptr(out)
+    o = _opts(ctx.lib, out_location=out_loc, **opts_kw)
+    rc = ctx.lib.plaidgpu_score(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(o), out_ptr)
+    if rc == L.ERR_NOOVERLAP:
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    ctx.check(rc)
+    return NamedMatrix(res, list(matG.colnames) if matG.colnames is not None else None,
+                       list(X.colnames) if X.colnames is not None else None)
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's functions
+# ---------------------------------------------------------------------------------------
+def plaid(X: NamedMatrix, matG: NamedMatrix, stats="mean", chunk=None, normalize=True, *, ctx=None, out=None):
+    """`plaid(X, matG, stats=c("mean","sum"), chunk=NULL, normalize=TRUE)` (R/plaid.R:60-87).
+    `chunk` is accepted and ignored, as in the reference (its value never reaches
+    chunked_crossprod, R/plaid.R:80).  Returns NamedMatrix(S x N) or None on no overlap."""
+    if isinstance(stats, (list, tuple)):
+        stats = stats[0]
+    return _score(X, matG, dict(scorer=L.PLAID, stats_mean=1 if stats == "mean" else 0,
+                                normalize=1 if normalize else 0), ctx, out)
+
+
+def chunked_crossprod(x, y, chunk=None, *, ctx=None):
+    """`chunked_crossprod(x, y, chunk=NULL)` (R/plaid.R:100-123): t(x) %*% y for a sparse x whose
+    non-zeros are constant within a column (the only form plaid() ever passes: G or
+    colScale(G, 1/sumG)).  Returns a dense S x N array (documented deviation: the reference
+    returns a Matrix-class object on its un-chunked branch).  The chunk message of the
+    reference is kept; device-side the product is tiled by columns independently of `chunk`."""
+    ctx = ctx or default_context()
+    xs = sp.csc_matrix(x)
+    xs.sort_indices()
+    S = xs.shape[1]
+    scale = np.ones(S)
+    d = xs.data
+    for s in range(S):
+        seg = d[xs.indptr[s]:xs.indptr[s + 1]]
+        seg = seg[seg != 0]
+        if seg.size:
+            if not np.all(seg == seg[0]):
+                raise ValueError("chunked_crossprod: x must be column-scaled binary (as plaid() builds it)")
+            scale[s] = seg[0]
+    if chunk is None or chunk < 0:
+        chunk = int(round(0.8 * 2147483647 / S))
+    ncol_y = y.shape[1] if getattr(y, "ndim", 2) == 2 else 1
+    if ncol_y >= chunk:
+        _message(f"[chunked_crossprod] chunked compute: chunk = {chunk}")
+    ctx.set_genesets(xs)
+    keep: list = []
+    M = _matrix_struct(y, keep)
+    if M.P != xs.shape[0]:
+        raise ValueError("non-conformable arguments")
+    rowmap = np.arange(M.P, dtype=np.int32)
+    res = np.empty((S, M.N), dtype=np.float64, order="F")
+    ctx.check(ctx.lib.plaidgpu_crossprod(ctx.h, C.byref(M), rowmap.ctypes.data, scale.ctypes.data, L.HOST,
+                                         res.ctypes.data))
+    return res
+
+
+def normalize_medians(x, ignore_zero: Optional[bool] = None, *, ctx=None):
+    """`normalize_medians(x, ignore.zero=NULL)` (R/plaid.R:554-575)."""
+    ctx = ctx or default_context()
+    a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+    if a.ndim == 1:
+        a = np.asfortranarray(a[:, None])
+    res = np.empty_like(a, order="F")
+    iz = -1 if ignore_zero is None else int(bool(ignore_zero))
+    ctx.check(ctx.lib.plaidgpu_normalize_medians(ctx.h, a.ctypes.data, a.shape[0], a.shape[1], iz, L.HOST,
+                                                 res.ctypes.data))
+    return res
+
+
+def sparse_colranks(X, signed: bool = False, ties_method: str = "average", *, ctx=None):
+    """`sparse_colranks(X, signed, ties.method)` (R/plaid.R:631-650): csc_matrix, same pattern."""
+    ctx = ctx or default_context()
+    if ties_method not in L.TIES:
+        raise ValueError(f"ties.method {ties_method!r} not supported on the GPU path (average, min, max)")
+    m = sp.csc_matrix(X).astype(np.float64)
+    m.sort_indices()
+    keep: list = []
+    M = _matrix_struct(m, keep)
+    r = np.empty(m.nnz, dtype=np.float64)
+    ctx.check(ctx.lib.plaidgpu_colranks(ctx.h, C.byref(M), L.TIES[ties_method], int(signed), 1, L.HOST,
+                                        r.ctypes.data))
+    return sp.csc_matrix((r, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+
+
+def colranks(X, sparse: Optional[bool] = None, signed: bool = False, keep_zero: bool = False,
+             ties_method: str = "average", *, ctx=None):
+    """`colranks(X, sparse=NULL, signed=FALSE, keep.zero=FALSE, ties.method="average")`
+    (R/plaid.R:589-623).  csc_matrix for (sparse & keep_zero), else a dense P x N array."""
+    ctx = ctx or default_context()
+    if ties_method not in L.TIES:
+        raise ValueError(f"ties.method {ties_method!r} not supported on the GPU path (average, min, max)")
+    is_sp = sp is not None and sp.issparse(X)
+    if sparse is None:
+        sparse = is_sp
+    if sparse and keep_zero:
+        return sparse_colranks(X, signed=signed, ties_method=ties_method, ctx=ctx)
+    keep: list = []
+    if sparse:
+        M = _matrix_struct(sp.csc_matrix(X), keep)
+    else:
+        M = _matrix_struct(X.toarray() if is_sp else X, keep)
+    res = np.empty((M.P, M.N), dtype=np.float64, order="F")
+    ctx.check(ctx.lib.plaidgpu_colranks(ctx.h, C.byref(M), L.TIES[ties_method], int(signed), 0, L.HOST,
+                                        res.ctypes.data))
+    return res
+
+
+def replaid_scse(X: NamedMatrix, matG: NamedMatrix, removeLog2: Optional[bool] = None, scoreMean: bool = False,
+                 *, ctx=None, out=None):
+    """`replaid.scse(X, matG, removeLog2=NULL, scoreMean=FALSE)` (R/plaid.R:155-190)."""
+    rl = -1 if removeLog2 is None else int(bool(removeLog2))
+    return _score(X, matG, dict(scorer=L.SCSE, remove_log2=rl, score_mean=int(bool(scoreMean))), ctx, out)
+
+
+def replaid_sing(X: NamedMatrix, matG: NamedMatrix, *, ctx=None, out=None):
+    """`replaid.sing(X, matG)` (R/plaid.R:213-219)."""
+    return _score(X, matG, dict(scorer=L.SING, nrow_x=int(X.shape[0])), ctx, out)
+
+
+def replaid_ssgsea(X: NamedMatrix, matG: NamedMatrix, alpha: float = 0.0, *, ctx=None, out=None):
+    """`replaid.ssgsea(X, matG, alpha=0)` (R/plaid.R:244-255)."""
+    return _score(X, matG, dict(scorer=L.SSGSEA, alpha=float(alpha)), ctx, out)
+
+
+def replaid_ucell(X: NamedMatrix, matG: NamedMatrix, rmax: float = 1500, *, ctx=None, out=None):
+    """`replaid.ucell(X, matG, rmax=1500)` (R/plaid.R:276-282)."""
+    return _score(X, matG, dict(scorer=L.UCELL, rmax=float(rmax)), ctx, out)
+
+
+def replaid_aucell(X: NamedMatrix, matG: NamedMatrix, aucMaxRank: Optional[float] = None, *, ctx=None, out=None):
+    """`replaid.aucell(X, matG, aucMaxRank=ceiling(0.05*nrow(X)))` (R/plaid.R:304-309)."""
+    a = float(aucMaxRank) if aucMaxRank is not None else float(math.ceil(0.05 * X.shape[0]))
+    return _score(X, matG, dict(scorer=L.AUCELL, auc_max_rank=a), ctx, out)

@@ -1,0 +1,826 @@
+// C ABI of libplaidgpu (include/plaidgpu.h): context, gene-set plan, the score pipeline
+// (rank -> score product -> median normalisation -> epilogue) and the stand-alone entry points.
+// Host-side orchestration only; the arithmetic is in score_kernels.cu / stats_kernels.cu /
+// rank_kernels.cu.  There is no CPU fallback: every entry point fails with PLAIDGPU_ERR_CUDA
+// when the GPU is unusable.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+using namespace plaidgpu;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct plaidgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_chunk[2] = {};
+  std::string err;
+  int64_t launches = 0;
+  double ms[4] = {0, 0, 0, 0};  // 0 score, 1 colstats, 2 fixup, 3 rank
+
+  // gene sets (host copy of the binary pattern)
+  bool have_g = false;
+  int32_t PG = 0, S = 0;
+  std::vector<int32_t> Gp, Gi;
+  std::vector<double> g_colsums;  // colSums(matG != 0) over all rows
+
+  // plan: adjacency of X rows, tiled by set range (depends on rowmap)
+  bool plan_ok = false;
+  int32_t plan_P = 0, plan_hint = 0;
+  std::vector<int32_t> plan_rowmap;
+  int32_t Ts = 0, T = 0;
+  LaunchCfg cfg{};
+  int64_t nnz_mapped = 0;
+  int32_t n_overlap = 0;
+  DevBuf d_ptr, d_idx, d_inv_mean, d_inv_one, d_ns, d_custom_inv, d_beta;
+
+  // current scoring call
+  bool in_call = false, computed = false;
+  plaidgpu_opts opts{};
+  bool dense = false;
+  int32_t P = 0;
+  int64_t N = 0, nnz = 0;
+  const int32_t* xp = nullptr;
+  const int32_t* xi = nullptr;
+  const double* xx = nullptr;
+  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32;
+  double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
+  bool need_norm = false;
+  std::vector<double> h_med_all, h_med_nz, h_colmin;
+  const double* score_vals = nullptr;  // what the score kernel reads as values
+  const double* score_r0 = nullptr;
+};
+
+namespace {
+
+int fail(plaidgpu_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int fail_cuda(plaidgpu_ctx* c, cudaError_t e, const char* where) {
+  if (c) c->err = std::string(where) + ": " + cudaGetErrorString(e);
+  return PLAIDGPU_ERR_CUDA;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return fail_cuda(c, _e, #call);    \
+  } while (0)
+
+// ---- plan ------------------------------------------------------------------------------
+int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_hint) {
+  if (c->plan_ok && c->plan_P == P && c->plan_hint == tile_hint &&
+      memcmp(c->plan_rowmap.data(), rowmap, sizeof(int32_t) * (size_t)P) == 0)
+    return PLAIDGPU_OK;
+  c->plan_ok = false;
+  const int32_t S = c->S, PG = c->PG;
+  std::vector<int32_t> g2x((size_t)PG, -1);
+  int32_t n_overlap = 0;
+  for (int32_t r = 0; r < P; ++r) {
+    const int32_t g = rowmap[r];
+    if (g < 0) continue;
+    if (g >= PG) return fail(c, PLAIDGPU_ERR_ARG, "rowmap entry out of range");
+    if (g2x[g] != -1) return fail(c, PLAIDGPU_ERR_ARG, "two rows of X map to the same gene-set row");
+    g2x[g] = r;
+    ++n_overlap;
+  }
+  c->n_overlap = n_overlap;
+  if (n_overlap == 0) return fail(c, PLAIDGPU_ERR_NOOVERLAP, "[plaid] ERROR. No overlapping features.");
+
+  int32_t Ts = 0, T = 0;
+  cudaError_t e = score_configure(c->device, S, tile_hint, &Ts, &T, &c->cfg);
+  if (e != cudaSuccess) return fail_cuda(c, e, "score_configure");
+
+  // CSR by X row; walking the sets in ascending order leaves every row's list sorted by set
+  std::vector<uint32_t> rowcnt((size_t)P + 1, 0);
+  std::vector<double> ns((size_t)S, 0.0);
+  for (int32_t s = 0; s < S; ++s)
+    for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+      const int32_t r = g2x[c->Gi[q]];
+      if (r >= 0) {
+        ++rowcnt[r + 1];
+        ns[s] += 1.0;
+      }
+    }
+  for (int32_t r = 0; r < P; ++r) rowcnt[r + 1] += rowcnt[r];
+  const int64_t nnzm = rowcnt[P];
+  std::vector<uint32_t> fill(rowcnt.begin(), rowcnt.end() - 1);
+  std::vector<uint16_t> idx((size_t)std::max<int64_t>(nnzm, 1));
+  std::vector<uint32_t> ptr((size_t)P * (T + 1));
+  std::vector<int32_t> setof((size_t)std::max<int64_t>(nnzm, 1));
+  for (int32_t s = 0; s < S; ++s)
+    for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+      const int32_t r = g2x[c->Gi[q]];
+      if (r >= 0) setof[fill[r]++] = s;
+    }
+  for (int32_t r = 0; r < P; ++r) {
+    uint32_t e0 = rowcnt[r];
+    const uint32_t e1 = rowcnt[r + 1];
+    uint32_t* pr = ptr.data() + (size_t)r * (T + 1);
+    for (int32_t t = 0; t < T; ++t) {
+      pr[t] = e0;
+      const int32_t hi = (t + 1) * Ts;
+      while (e0 < e1 && setof[e0] < hi) {
+        idx[e0] = (uint16_t)(setof[e0] - t * Ts);
+        ++e0;
+      }
+    }
+    pr[T] = e1;
+  }
+  std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
+  for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76
+
+  CK(c->d_ptr.reserve(ptr.size() * sizeof(uint32_t)));
+  CK(c->d_idx.reserve(idx.size() * sizeof(uint16_t)));
+  CK(c->d_inv_mean.reserve((size_t)S * sizeof(double)));
+  CK(c->d_inv_one.reserve((size_t)S * sizeof(double)));
+  CK(c->d_ns.reserve((size_t)S * sizeof(double)));
+  CK(cudaMemcpyAsync(c->d_ptr.p, ptr.data(), ptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_inv_mean.p, inv_mean.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_inv_one.p, inv_one.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_ns.p, ns.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
+  c->Ts = Ts;
+  c->T = T;
+  c->nnz_mapped = nnzm;
+  c->plan_P = P;
+  c->plan_hint = tile_hint;
+  c->plan_rowmap.assign(rowmap, rowmap + P);
+  c->plan_ok = true;
+  return PLAIDGPU_OK;
+}
+
+// bring a caller buffer onto the device (or alias it when it already is there)
+template <typename T>
+int to_device(plaidgpu_ctx* c, const T* src, size_t n, int location, DevBuf& buf, const T** out) {
+  if (location == PLAIDGPU_DEVICE) {
+    *out = src;
+    return PLAIDGPU_OK;
+  }
+  CK(buf.reserve(std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) CK(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  *out = buf.as<T>();
+  return PLAIDGPU_OK;
+}
+
+int device_minmax(plaidgpu_ctx* c, const double* d, int64_t n, double* mn, double* mx) {
+  CK(c->b_scal.reserve(4 * sizeof(double)));
+  CK(launch_minmax(d, n, c->b_scal.as<double>(), c->stream));
+  c->launches += (n > 0) ? 3 : 2;
+  double h[2];
+  CK(cudaMemcpyAsync(h, c->b_scal.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *mn = h[0];
+  *mx = h[1];
+  return PLAIDGPU_OK;
+}
+
+int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X) {
+  c->dense = (X->kind == PLAIDGPU_DENSE);
+  c->P = X->P;
+  c->N = X->N;
+  if (X->P <= 0 || X->N < 0) return fail(c, PLAIDGPU_ERR_ARG, "bad matrix dimensions");
+  if (c->dense) {
+    if (!X->x && X->N > 0) return fail(c, PLAIDGPU_ERR_ARG, "dense X without values");
+    c->nnz = (int64_t)X->P * X->N;
+    c->xp = nullptr;
+    c->xi = nullptr;
+    int rc = to_device<double>(c, X->x, (size_t)c->nnz, X->location, c->b_xx, &c->xx);
+    if (rc) return rc;
+  } else if (X->kind == PLAIDGPU_CSC) {
+    if (!X->p) return fail(c, PLAIDGPU_ERR_ARG, "CSC X without column pointers");
+    int32_t last = 0;
+    if (X->location == PLAIDGPU_HOST) {
+      last = X->p[X->N];
+    } else {
+      CK(cudaMemcpyAsync(&last, X->p + X->N, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    c->nnz = last;
+    int rc = to_device<int32_t>(c, X->p, (size_t)X->N + 1, X->location, c->b_xp, &c->xp);
+    if (rc) return rc;
+    rc = to_device<int32_t>(c, X->i, (size_t)c->nnz, X->location, c->b_xi, &c->xi);
+    if (rc) return rc;
+    rc = to_device<double>(c, X->x, (size_t)c->nnz, X->location, c->b_xx, &c->xx);
+    if (rc) return rc;
+  } else {
+    return fail(c, PLAIDGPU_ERR_ARG, "unknown matrix kind");
+  }
+  return PLAIDGPU_OK;
+}
+
+bool is_rank_scorer(int s) {
+  return s == PLAIDGPU_SING || s == PLAIDGPU_SSGSEA || s == PLAIDGPU_UCELL || s == PLAIDGPU_AUCELL;
+}
+
+int max_col_nnz(plaidgpu_ctx* c, int32_t* out) {
+  CK(c->b_i32.reserve(sizeof(int32_t)));
+  CK(launch_max_col_nnz(c->xp, c->N, c->b_i32.as<int32_t>(), c->stream));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out, c->b_i32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PLAIDGPU_OK;
+}
+
+double r_mean(const double* v, int64_t n) {  // base::mean(na.rm = TRUE): long double, one refinement
+  long double s = 0.0L;
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (v[i] == v[i]) {
+      s += v[i];
+      ++m;
+    }
+  if (m == 0) return NAN;
+  s /= (long double)m;
+  long double t = 0.0L;
+  for (int64_t i = 0; i < n; ++i)
+    if (v[i] == v[i]) t += (v[i] - s);
+  return (double)(s + t / (long double)m);
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int plaidgpu_version(void) { return PLAIDGPU_VERSION; }
+
+void plaidgpu_default_opts(plaidgpu_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->scorer = PLAIDGPU_PLAID;
+  o->stats_mean = 1;
+  o->normalize = 1;
+  o->ignore_zero = -1;
+  o->remove_log2 = -1;
+  o->score_mean = 0;
+  o->out_location = PLAIDGPU_HOST;
+  o->tile_sets = 0;
+  o->alpha = 0.0;
+  o->rmax = 1500.0;
+  o->auc_max_rank = 0.0;
+  o->tau = 0.0;
+  o->nrow_x = 0;
+  o->matg_full_colsums = nullptr;
+}
+
+int plaidgpu_init(int device, plaidgpu_ctx** out) {
+  if (!out) return PLAIDGPU_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return PLAIDGPU_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PLAIDGPU_ERR_CUDA;
+  if (prop.major < 10) return PLAIDGPU_ERR_CUDA;  // sm_100a code only
+  plaidgpu_ctx* c = new (std::nothrow) plaidgpu_ctx();
+  if (!c) return PLAIDGPU_ERR_NOMEM;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return PLAIDGPU_ERR_CUDA;
+  }
+  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  for (auto& ev : c->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  *out = c;
+  return PLAIDGPU_OK;
+}
+
+void plaidgpu_destroy(plaidgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
+                    &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
+                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+const char* plaidgpu_last_error(const plaidgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int64_t plaidgpu_launch_count(const plaidgpu_ctx* c) { return c ? c->launches : 0; }
+void plaidgpu_reset_launch_count(plaidgpu_ctx* c) { if (c) c->launches = 0; }
+double plaidgpu_last_kernel_ms(const plaidgpu_ctx* c, int which) {
+  return (c && which >= 0 && which < 4) ? c->ms[which] : -1.0;
+}
+void* plaidgpu_stream(const plaidgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int plaidgpu_plan_info(const plaidgpu_ctx* c, int32_t* tile_sets, int32_t* n_tiles, int64_t* nnz_mapped,
+                       int32_t* warps_per_cta, int32_t* ctas) {
+  if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
+  if (tile_sets) *tile_sets = c->Ts;
+  if (n_tiles) *n_tiles = c->T;
+  if (nnz_mapped) *nnz_mapped = c->nnz_mapped;
+  if (warps_per_cta) *warps_per_cta = c->cfg.warps;
+  if (ctas) *ctas = c->cfg.ctas;
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_set_genesets(plaidgpu_ctx* c, int32_t P_G, int32_t S, const int32_t* Gp, const int32_t* Gi,
+                          const double* Gx) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (P_G <= 0 || S <= 0 || !Gp || (!Gi && Gp[S] > 0)) return fail(c, PLAIDGPU_ERR_ARG, "bad gene-set matrix");
+  c->have_g = false;
+  c->plan_ok = false;
+  c->PG = P_G;
+  c->S = S;
+  c->Gp.assign((size_t)S + 1, 0);
+  c->Gi.clear();
+  c->Gi.reserve((size_t)Gp[S]);
+  c->g_colsums.assign((size_t)S, 0.0);
+  for (int32_t s = 0; s < S; ++s) {
+    if (Gp[s + 1] < Gp[s]) return fail(c, PLAIDGPU_ERR_ARG, "gene-set column pointers not monotone");
+    for (int32_t q = Gp[s]; q < Gp[s + 1]; ++q) {
+      if (Gx && !(Gx[q] != 0.0)) continue;  // 1 * (matG != 0): explicit zeros drop out (R/plaid.R:73)
+      if (Gi[q] < 0 || Gi[q] >= P_G) return fail(c, PLAIDGPU_ERR_ARG, "gene-set row index out of range");
+      c->Gi.push_back(Gi[q]);
+      c->g_colsums[s] += 1.0;
+    }
+    c->Gp[s + 1] = (int32_t)c->Gi.size();
+  }
+  c->have_g = true;
+  return PLAIDGPU_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap,
+                         const plaidgpu_opts* opts, plaidgpu_scalars* local) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !rowmap || !opts || !local) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_set_genesets has not been called");
+  CK(cudaSetDevice(c->device));
+  c->in_call = false;
+  c->computed = false;
+  c->opts = *opts;
+  if (opts->scorer < PLAIDGPU_PLAID || opts->scorer > PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
+  if (opts->scorer == PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva is not available in this build");
+  if (opts->scorer == PLAIDGPU_SSGSEA && !(1.0 + opts->alpha > 0.0)) return fail(c, PLAIDGPU_ERR_ARG, "ssgsea needs alpha > -1");
+  int rc = build_plan(c, X->P, rowmap, opts->tile_sets);
+  if (rc) return rc;
+  rc = load_matrix(c, X);
+  if (rc) return rc;
+
+  memset(local, 0, sizeof(*local));
+  local->x_min = INFINITY;
+  local->x_max = -INFINITY;
+  local->score_min = INFINITY;
+  local->ignore_zero = -1;
+  c->score_vals = c->xx;
+  c->score_r0 = nullptr;
+
+  if (opts->scorer == PLAIDGPU_SCSE && opts->remove_log2 < 0) {  // R/plaid.R:160-161
+    double mn, mx;
+    rc = device_minmax(c, c->xx, c->nnz, &mn, &mx);
+    if (rc) return rc;
+    if (!c->dense && c->nnz < (int64_t)c->P * c->N) {  // implicit zeros take part in min / max
+      mn = fmin(mn, 0.0);
+      mx = fmax(mx, 0.0);
+    }
+    local->x_min = mn;
+    local->x_max = mx;
+  }
+
+  if (is_rank_scorer(opts->scorer)) {
+    const int ties = (opts->scorer == PLAIDGPU_SING) ? PLAIDGPU_TIES_MIN : PLAIDGPU_TIES_AVERAGE;
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+    CK(c->b_colmax.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    if (c->dense) {
+      // colranks() dense branch for every rank scorer (R/plaid.R:617)
+      CK(launch_rank_dense(c->xx, c->P, c->N, ties, 0, c->b_rank.as<double>(), c->b_colmax.as<double>(), c->stream));
+    } else {
+      int32_t mcn = 0;
+      rc = max_col_nnz(c, &mcn);
+      if (rc) return rc;
+      CK(c->b_r0.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+      // ssgsea: sparse_colranks (keep.zero = TRUE) ranks the stored entries only (R/plaid.R:245, 601);
+      // sing / ucell / aucell: dense-semantics ranks with the zero group (R/plaid.R:608)
+      const int dense_sem = (opts->scorer == PLAIDGPU_SSGSEA) ? 0 : 1;
+      CK(launch_rank_csc(c->xp, c->xx, c->P, c->N, ties, 0, dense_sem, c->b_rank.as<double>(),
+                         c->b_r0.as<double>(), c->b_colmax.as<double>(), mcn, c->stream));
+      c->score_r0 = c->b_r0.as<double>();
+    }
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    double mn, mx;
+    rc = device_minmax(c, c->b_colmax.as<double>(), c->N, &mn, &mx);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+    c->ms[3] = ms;
+    local->rank_max = mx;
+    c->score_vals = c->b_rank.as<double>();
+  }
+  c->in_call = true;
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!scal) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!c->in_call) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_begin has not been called");
+  CK(cudaSetDevice(c->device));
+  const plaidgpu_opts& o = c->opts;
+
+  ScoreParams p{};
+  p.xp = c->xp;
+  p.xi = c->xi;
+  p.xx = c->score_vals;
+  p.r0 = nullptr;
+  p.P = c->P;
+  p.N = c->N;
+  p.ptr = c->d_ptr.as<uint32_t>();
+  p.idx = c->d_idx.as<uint16_t>();
+  p.ns = c->d_ns.as<double>();
+  p.S = c->S;
+  p.T = c->T;
+  p.Ts = c->Ts;
+  p.mode = XF_IDENT;
+  p.a0 = p.a1 = 0.0;
+  p.colnorm = 0;
+  p.ld = c->S;
+  bool mean = true;
+  c->need_norm = false;
+  switch (o.scorer) {
+    case PLAIDGPU_PLAID:
+      mean = o.stats_mean != 0;
+      c->need_norm = o.normalize != 0;
+      break;
+    case PLAIDGPU_SCSE: {
+      const bool rl = o.remove_log2 < 0 ? (scal->x_min == 0.0 && scal->x_max < 20.0) : (o.remove_log2 != 0);
+      if (rl) p.mode = c->dense ? XF_EXP2_POS : XF_EXP2;
+      mean = o.score_mean != 0;
+      p.colnorm = o.score_mean ? 2 : 1;
+      break;
+    }
+    case PLAIDGPU_SING:
+      p.mode = XF_SING;
+      p.a0 = (double)(o.nrow_x > 0 ? o.nrow_x : c->P);
+      break;
+    case PLAIDGPU_SSGSEA:
+      p.mode = XF_SSGSEA;
+      p.a1 = o.alpha;
+      p.a0 = (o.alpha != 0.0) ? pow(scal->rank_max, 1.0 + o.alpha) : scal->rank_max;
+      c->need_norm = true;
+      break;
+    case PLAIDGPU_UCELL:
+      p.mode = XF_UCELL;
+      p.a0 = scal->rank_max;
+      p.a1 = o.rmax + 1.0;
+      c->need_norm = true;
+      break;
+    case PLAIDGPU_AUCELL:
+      p.mode = XF_AUCELL;
+      p.a0 = scal->rank_max;
+      p.a1 = o.auc_max_rank > 0.0 ? o.auc_max_rank : ceil(0.05 * (double)c->P);
+      c->need_norm = true;
+      break;
+    default:
+      return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
+  }
+  p.inv = mean ? c->d_inv_mean.as<double>() : c->d_inv_one.as<double>();
+  if (is_rank_scorer(o.scorer)) {
+    if (c->dense) {
+      // dense input: transform the dense rank matrix in place, then plain product
+      CK(launch_xform_dense(c->b_rank.as<double>(), c->b_rank.as<double>(), c->nnz, p.mode, p.a0, p.a1, c->stream));
+      c->launches += 1;
+      p.mode = XF_IDENT;
+    } else {
+      p.r0 = c->score_r0;  // nullptr for ssgsea: zeros rank 0
+      if (o.scorer == PLAIDGPU_SSGSEA) p.r0 = nullptr;
+    }
+  }
+
+  // where the raw scores go
+  const int64_t total = (int64_t)c->S * c->N;
+  if (o.out_location == PLAIDGPU_DEVICE) {
+    if (!out && total > 0) return fail(c, PLAIDGPU_ERR_ARG, "device output buffer required by plaidgpu_score_compute");
+    c->raw = out;  // raw scores land in the caller's buffer; finish fixes them up in place
+  } else {
+    CK(c->b_raw.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+    c->raw = c->b_raw.as<double>();
+  }
+  p.out = c->raw;
+
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  CK(launch_score(p, c->dense, c->cfg, c->stream));
+  c->launches += 1;
+  CK(cudaEventRecord(c->ev[1], c->stream));
+
+  scal->score_min = INFINITY;
+  if (c->need_norm) {
+    CK(c->b_med_all.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    CK(c->b_med_nz.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    CK(c->b_colmin.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    CK(launch_colstats(c->raw, c->S, c->S, c->N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(),
+                       c->b_colmin.as<double>(), c->stream));
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    c->h_med_all.resize((size_t)c->N);
+    c->h_med_nz.resize((size_t)c->N);
+    c->h_colmin.resize((size_t)c->N);
+    if (c->N) {
+      CK(cudaMemcpyAsync(c->h_med_all.data(), c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->h_med_nz.data(), c->b_med_nz.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->h_colmin.data(), c->b_colmin.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->ms[0] = ms;
+  if (c->need_norm) {
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+    c->ms[1] = ms;
+    double mn = INFINITY;
+    for (int64_t j = 0; j < c->N; ++j) mn = fmin(mn, c->h_colmin[j]);
+    scal->score_min = mn;
+  }
+  c->computed = true;
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_get_col_medians(plaidgpu_ctx* c, double* med_all, double* med_nz) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!c->computed || !c->need_norm) return fail(c, PLAIDGPU_ERR_STATE, "no medians: run plaidgpu_score_compute with normalisation");
+  if (med_all) memcpy(med_all, c->h_med_all.data(), (size_t)c->N * sizeof(double));
+  if (med_nz) memcpy(med_nz, c->h_med_nz.data(), (size_t)c->N * sizeof(double));
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double* med_all, const double* med_nz,
+                             int64_t N_total, plaidgpu_scalars* scal) {
+  if (!scal || !med_all || !med_nz || N_total < 0) return PLAIDGPU_ERR_ARG;
+  const int iz = ignore_zero_opt < 0 ? (score_min == 0.0 ? 1 : 0) : (ignore_zero_opt != 0);  // R/plaid.R:556-557
+  scal->ignore_zero = iz;
+  scal->score_min = score_min;
+  scal->med_mean = r_mean(iz ? med_nz : med_all, N_total);  // R/plaid.R:572
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!scal || (!out && c->N > 0)) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!c->computed) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_compute has not been called");
+  CK(cudaSetDevice(c->device));
+  const plaidgpu_opts& o = c->opts;
+  const int32_t S = c->S;
+  const int64_t N = c->N;
+
+  double alpha = 1.0, cc = 0.0;
+  const double* med = nullptr;
+  const double* beta = nullptr;
+  bool fix = false;
+  if (c->need_norm) {
+    med = scal->ignore_zero ? c->b_med_nz.as<double>() : c->b_med_all.as<double>();
+    cc = scal->med_mean;
+    fix = true;
+  }
+  if (o.scorer == PLAIDGPU_UCELL) {  // 1 - S/rmax + (colSums(matG != 0) + 1) / (2 rmax)   (R/plaid.R:280)
+    std::vector<double> b((size_t)S);
+    const double* gs = o.matg_full_colsums ? o.matg_full_colsums : c->g_colsums.data();
+    for (int32_t s = 0; s < S; ++s) b[s] = 1.0 + (gs[s] + 1.0) / (2.0 * o.rmax);
+    CK(c->d_beta.reserve((size_t)S * sizeof(double)));
+    CK(cudaMemcpyAsync(c->d_beta.p, b.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    beta = c->d_beta.as<double>();
+    alpha = -1.0 / o.rmax;
+    fix = true;
+  }
+
+  CK(cudaEventRecord(c->ev[4], c->stream));
+  if (o.out_location == PLAIDGPU_DEVICE) {
+    if (out != c->raw) return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_finish: device `out` differs from the buffer given to compute");
+    if (fix) {
+      CK(launch_fixup(c->raw, out, S, S, 0, N, med, cc, alpha, beta, c->stream));
+      c->launches += 1;
+    }
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  } else {
+    // host output: fix up a block of columns, then stream it out while the next block is fixed
+    int64_t chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / ((int64_t)S * 8));
+    int k = 0;
+    for (int64_t j0 = 0; j0 < N; j0 += chunk, ++k) {
+      const int64_t j1 = std::min<int64_t>(N, j0 + chunk);
+      if (fix) {
+        CK(launch_fixup(c->raw, c->raw, S, S, j0, j1, med, cc, alpha, beta, c->stream));
+        c->launches += 1;
+      }
+      CK(cudaEventRecord(c->ev_chunk[k & 1], c->stream));
+      CK(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k & 1], 0));
+      CK(cudaMemcpyAsync(out + j0 * S, c->raw + j0 * S, (size_t)(j1 - j0) * S * sizeof(double),
+                         cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->ms[2] = ms;
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
+                   double* out) {
+  plaidgpu_scalars s;
+  int rc = plaidgpu_score_begin(c, X, rowmap, opts, &s);
+  if (rc) return rc;
+  rc = plaidgpu_score_compute(c, &s, out);
+  if (rc) return rc;
+  if (c->need_norm) {
+    rc = plaidgpu_combine_medians(opts->ignore_zero, s.score_min, c->h_med_all.data(), c->h_med_nz.data(), c->N, &s);
+    if (rc) return fail(c, rc, "combine_medians failed");
+  }
+  return plaidgpu_score_finish(c, &s, out);
+}
+
+int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t* rowmap, const double* colscale,
+                       int out_location, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!Y || !rowmap) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_set_genesets has not been called");
+  plaidgpu_opts o;
+  plaidgpu_default_opts(&o);
+  o.stats_mean = 0;
+  o.normalize = 0;
+  o.out_location = out_location;
+  plaidgpu_scalars s;
+  int rc = plaidgpu_score_begin(c, Y, rowmap, &o, &s);
+  if (rc) return rc;
+  if (colscale) {  // swap the per-set scale for the caller's column scale of x
+    CK(c->d_custom_inv.reserve((size_t)c->S * sizeof(double)));
+    CK(cudaMemcpyAsync(c->d_custom_inv.p, colscale, (size_t)c->S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::swap(c->d_inv_one.p, c->d_custom_inv.p);
+    std::swap(c->d_inv_one.cap, c->d_custom_inv.cap);
+  }
+  rc = plaidgpu_score_compute(c, &s, out);
+  if (colscale) {
+    std::swap(c->d_inv_one.p, c->d_custom_inv.p);
+    std::swap(c->d_inv_one.cap, c->d_custom_inv.cap);
+  }
+  if (rc) return rc;
+  return plaidgpu_score_finish(c, &s, out);
+}
+
+// -----------------------------------------------------------------------------------------
+int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int is_signed, int keep_zero,
+                      int out_location, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (ties < PLAIDGPU_TIES_AVERAGE || ties > PLAIDGPU_TIES_MAX) return fail(c, PLAIDGPU_ERR_ARG, "unsupported ties.method");
+  CK(cudaSetDevice(c->device));
+  c->in_call = false;
+  c->computed = false;
+  int rc = load_matrix(c, X);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev[6], c->stream));
+  if (c->dense) {
+    double* dst = out;
+    if (out_location == PLAIDGPU_HOST) {
+      CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+      dst = c->b_rank.as<double>();
+    }
+    CK(launch_rank_dense(c->xx, c->P, c->N, ties, is_signed, dst, nullptr, c->stream));
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    if (out_location == PLAIDGPU_HOST && c->nnz)
+      CK(cudaMemcpyAsync(out, dst, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    int32_t mcn = 0;
+    rc = max_col_nnz(c, &mcn);
+    if (rc) return rc;
+    if (keep_zero) {  // sparse_colranks: nnz ranks
+      double* dst = out;
+      if (out_location == PLAIDGPU_HOST) {
+        CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+        dst = c->b_rank.as<double>();
+      }
+      CK(launch_rank_csc(c->xp, c->xx, c->P, c->N, ties, is_signed, 0, dst, nullptr, nullptr, mcn, c->stream));
+      c->launches += 1;
+      CK(cudaEventRecord(c->ev[7], c->stream));
+      if (out_location == PLAIDGPU_HOST && c->nnz)
+        CK(cudaMemcpyAsync(out, dst, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else {  // dense P x N ranks with the zero group
+      CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+      CK(c->b_r0.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+      CK(launch_rank_csc(c->xp, c->xx, c->P, c->N, ties, is_signed, 1, c->b_rank.as<double>(),
+                         c->b_r0.as<double>(), nullptr, mcn, c->stream));
+      const int64_t total = (int64_t)c->P * c->N;
+      double* dst = out;
+      if (out_location == PLAIDGPU_HOST) {
+        CK(c->b_raw.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+        dst = c->b_raw.as<double>();
+      }
+      CK(launch_expand_ranks(c->xp, c->xi, c->b_rank.as<double>(), c->b_r0.as<double>(), c->P, c->N, dst, c->stream));
+      c->launches += 2;
+      CK(cudaEventRecord(c->ev[7], c->stream));
+      if (out_location == PLAIDGPU_HOST && total)
+        CK(cudaMemcpyAsync(out, dst, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+  c->ms[3] = ms;
+  return PLAIDGPU_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int64_t N, int ignore_zero,
+                               int location, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (S <= 0 || N < 0 || (N > 0 && (!x || !out))) return fail(c, PLAIDGPU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  c->in_call = false;
+  c->computed = false;
+  const int64_t total = (int64_t)S * N;
+  const double* dx = x;
+  if (location == PLAIDGPU_HOST) {
+    CK(c->b_raw.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+    if (total) CK(cudaMemcpyAsync(c->b_raw.p, x, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dx = c->b_raw.as<double>();
+  }
+  CK(c->b_med_all.reserve(std::max<int64_t>(N, 1) * sizeof(double)));
+  CK(c->b_med_nz.reserve(std::max<int64_t>(N, 1) * sizeof(double)));
+  CK(c->b_colmin.reserve(std::max<int64_t>(N, 1) * sizeof(double)));
+  CK(cudaEventRecord(c->ev[2], c->stream));
+  CK(launch_colstats(dx, S, S, N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(), c->b_colmin.as<double>(), c->stream));
+  c->launches += 1;
+  CK(cudaEventRecord(c->ev[3], c->stream));
+  c->h_med_all.resize((size_t)N);
+  c->h_med_nz.resize((size_t)N);
+  c->h_colmin.resize((size_t)N);
+  if (N) {
+    CK(cudaMemcpyAsync(c->h_med_all.data(), c->b_med_all.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_med_nz.data(), c->b_med_nz.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_colmin.data(), c->b_colmin.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->ms[1] = ms;
+  double mn = INFINITY;
+  for (int64_t j = 0; j < N; ++j) mn = fmin(mn, c->h_colmin[j]);
+  plaidgpu_scalars s{};
+  plaidgpu_combine_medians(ignore_zero, mn, c->h_med_all.data(), c->h_med_nz.data(), N, &s);
+  const double* med = s.ignore_zero ? c->b_med_nz.as<double>() : c->b_med_all.as<double>();
+  CK(cudaEventRecord(c->ev[4], c->stream));
+  if (location == PLAIDGPU_DEVICE) {
+    CK(launch_fixup(dx, out, S, S, 0, N, med, s.med_mean, 1.0, nullptr, c->stream));
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[5], c->stream));
+  } else {
+    CK(launch_fixup(dx, c->b_raw.as<double>(), S, S, 0, N, med, s.med_mean, 1.0, nullptr, c->stream));
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    if (total) CK(cudaMemcpyAsync(out, c->b_raw.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->ms[2] = ms;
+  return PLAIDGPU_OK;
+}
+
+}  // extern "C"

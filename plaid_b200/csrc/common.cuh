@@ -1,0 +1,126 @@
+// Shared declarations of libplaidgpu (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/plaidgpu.h"
+
+namespace plaidgpu {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- value transforms applied when a stored entry of X is loaded -----------------------
+// (per stored entry, not per accumulate: the scatter loop only ever sees the result)
+enum XformMode : int {
+  XF_IDENT = 0,     // plaid(): x
+  XF_EXP2 = 1,      // replaid.scse sparse: 2^x on every stored entry (R/plaid.R:165-166)
+  XF_EXP2_POS = 2,  // replaid.scse dense: 2^x where x > 0 (R/plaid.R:168-169)
+  XF_SING = 3,      // r / a0 - 0.5, a0 = nrow(X)                         (R/plaid.R:216)
+  XF_SSGSEA = 4,    // r^(1+a1) / a0 - 0.5, a0 = max(r^(1+a1))            (R/plaid.R:246-251)
+  XF_UCELL = 5,     // min(a0 - r, a1), a0 = max(r), a1 = rmax + 1         (R/plaid.R:278)
+  XF_AUCELL = 6     // 1.08 * max((r - (a0 - a1)) / a1, 0), a1 = aucMaxRank (R/plaid.R:306)
+};
+
+struct ScoreParams {
+  // X shard (device): CSC (xp/xi/xx) or dense column-major (xx only)
+  const int32_t* xp;
+  const int32_t* xi;
+  const double* xx;   // values; for rank scorers the per-entry rank array instead
+  const double* r0;   // rank scorers: rank of the zero group per column [N] (else nullptr)
+  int32_t P;
+  int64_t N;
+  // gene-set plan (device): adjacency of every X row, tiled by set range
+  const uint32_t* ptr;  // [P * (T + 1)] offsets into idx
+  const uint16_t* idx;  // [nnz_mapped] set id local to its tile
+  const double* inv;    // [S] epilogue scale per set: 1/(n_s + 1e-8) ("mean") or 1 ("sum")
+  const double* ns;     // [S] n_s as double
+  int32_t S, T, Ts;
+  // transform
+  int32_t mode;
+  double a0, a1;
+  // scse column normalisation: 0 none, 1 = 100/(sum|x|+1e-8), 2 = 1/(mean|x|+1e-8)
+  int32_t colnorm;
+  // output, column-major S x N, leading dimension ld
+  double* out;
+  int64_t ld;
+};
+
+struct LaunchCfg {
+  int warps;       // warps per CTA
+  int ctas;        // persistent grid size
+  size_t smem;     // dynamic shared memory per CTA
+};
+
+// score_kernels.cu
+cudaError_t score_configure(int device, int32_t S, int32_t tile_sets_hint, int32_t* Ts, int32_t* T,
+                            LaunchCfg* cfg);
+cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st);
+
+// stats_kernels.cu
+// per-column statistics of a dense S x N matrix (ld = leading dimension):
+//   med_all[j]: median over non-NaN values (NaN when none)
+//   med_nz[j] : median over non-NaN, non-zero values (0 when none)        (R/plaid.R:561-566)
+//   colmin[j] : min over non-NaN values (+inf when none)
+cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
+                            double* med_nz, double* colmin, cudaStream_t st);
+// out[s,j] = alpha * (x[s,j] - med[j] + c) + (beta ? beta[s] : 0); med may be nullptr (then 0)
+cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, int64_t j0, int64_t j1,
+                         const double* med, double c, double alpha, const double* beta,
+                         cudaStream_t st);
+// global min / max of a device array of n doubles, NaN ignored (na.rm = TRUE); res[0]=min res[1]=max
+cudaError_t launch_minmax(const double* x, int64_t n, double* res2, cudaStream_t st);
+
+// rank_kernels.cu
+// Column ranks of the stored entries of a CSC matrix.
+//   dense_semantics = 0: rank among stored entries only (sparse_colranks, R/plaid.R:631-650)
+//   dense_semantics = 1: rank among all P entries of the column with the implicit zeros taking
+//                        part as the value 0 (sparseMatrixStats::colRanks, R/plaid.R:605,608);
+//                        r0[j] receives the rank of the zero group (also for columns without
+//                        implicit zeros: the rank an additional zero would tie into is not
+//                        needed then and r0 is set from the stored zeros or 0).
+//   is_signed: rank abs(x), multiply by sign(x)                          (R/plaid.R:603-606,637-640)
+// rank[nnz] out (may alias nothing), colmax[N] = max |rank| of the column incl. zero group.
+cudaError_t launch_rank_csc(const int32_t* xp, const double* xx, int32_t P, int64_t N, int ties,
+                            int is_signed, int dense_semantics, double* rank, double* r0,
+                            double* colmax, int32_t max_col_nnz, cudaStream_t st);
+// Dense column ranks (matrixStats::colRanks, R/plaid.R:614,617): x, rank: P x N column-major.
+cudaError_t launch_rank_dense(const double* x, int32_t P, int64_t N, int ties, int is_signed,
+                              double* rank, double* colmax, cudaStream_t st);
+// expand CSC ranks to a dense P x N matrix, implicit zeros -> r0[j] (or 0 when r0 == nullptr)
+cudaError_t launch_expand_ranks(const int32_t* xp, const int32_t* xi, const double* rank,
+                                const double* r0, int32_t P, int64_t N, double* dense,
+                                cudaStream_t st);
+// elementwise transform of a dense matrix with an XformMode (rank scorers on dense input)
+cudaError_t launch_xform_dense(const double* in, double* out, int64_t n, int mode, double a0,
+                               double a1, cudaStream_t st);
+// max nnz of any column of a device CSC pointer array
+cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st);
+
+// shared device helpers ------------------------------------------------------------------
+__device__ __forceinline__ double xform_value(int mode, double v, double a0, double a1) {
+  switch (mode) {
+    case XF_EXP2: return exp2(v);
+    case XF_EXP2_POS: return v > 0.0 ? exp2(v) : v;
+    case XF_SING: return v / a0 - 0.5;
+    case XF_SSGSEA: return (a1 != 0.0 ? pow(v, 1.0 + a1) : v) / a0 - 0.5;
+    case XF_UCELL: return fmin(a0 - v, a1);
+    case XF_AUCELL: return 1.08 * fmax((v - (a0 - a1)) / a1, 0.0);
+    default: return v;
+  }
+}
+
+// order-preserving 64-bit key of a double; -0 and +0 share one key
+__device__ __forceinline__ unsigned long long key_of(double v) {
+  if (v == 0.0) v = 0.0;
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+}  // namespace plaidgpu

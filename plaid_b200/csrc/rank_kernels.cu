@@ -1,0 +1,329 @@
+// K3/K4 — column ranks with ties, the ranking path of colranks() / sparse_colranks()
+// (reference R/plaid.R:589-650; base::rank, sparseMatrixStats::colRanks, matrixStats::colRanks).
+//
+// One CTA sorts one column: order-preserving 64-bit keys + original positions live in shared
+// memory (global workspace only when a column does not fit), sorted by an all-ascending bitonic
+// network over the next power of two with VIRTUAL +inf padding (pairs whose upper index is >= n
+// are skipped, which is exact because every compare-exchange moves the minimum down).  Ranks
+// come from the tie run [first, last] of each key found by binary search in the sorted column:
+// average = (first + last + 1) / 2, min = first + 1, max = last  (exact multiples of 0.5).
+// The implicit zeros of a CSC column never get materialised: they form one tie group whose
+// size is P - nnz, which only shifts the ranks of the positive entries.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace plaidgpu {
+
+namespace {
+
+constexpr int RT = 256;
+constexpr unsigned long long ZERO_KEY = 0x8000000000000000ull;
+constexpr unsigned long long NAN_KEY = ~0ull;
+
+template <typename PosT>
+__device__ __forceinline__ void cas(unsigned long long* k, PosT* p, int i, int l) {
+  const unsigned long long a = k[i], b = k[l];
+  if (a > b) {
+    k[i] = b;
+    k[l] = a;
+    const PosT t = p[i];
+    p[i] = p[l];
+    p[l] = t;
+  }
+}
+
+template <typename PosT>
+__device__ void bitonic_sort(unsigned long long* k, PosT* p, int n) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const int half = np2 >> 1;
+  for (int size = 2; size <= np2; size <<= 1) {
+    const int hs = size >> 1;
+    for (int q = threadIdx.x; q < half; q += blockDim.x) {  // flip step
+      const int blk = q / hs, o = q - blk * hs;
+      const int i = blk * size + o, l = blk * size + size - 1 - o;
+      if (l < n) cas(k, p, i, l);
+    }
+    __syncthreads();
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+      for (int q = threadIdx.x; q < half; q += blockDim.x) {
+        const int i = 2 * stride * (q / stride) + (q % stride), l = i + stride;
+        if (l < n) cas(k, p, i, l);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int lower_bound(const unsigned long long* k, int n, unsigned long long v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (k[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound(const unsigned long long* k, int n, unsigned long long v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (k[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct RankParams {
+  const int32_t* xp;  // nullptr: dense column-major input
+  const double* xx;
+  int32_t P;
+  int64_t N;
+  int ties, is_signed, dense_sem;
+  double* rank;
+  double* r0;
+  double* colmax;
+  unsigned long long* ws_keys;  // global workspace (GLOBAL_WS only)
+  void* ws_pos;
+  int cap;  // shared-memory capacity in elements (!GLOBAL_WS)
+};
+
+template <typename PosT, bool GLOBAL_WS>
+__global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
+  extern __shared__ unsigned long long rsm[];
+  __shared__ int s_nnan;
+  __shared__ double s_max[RT / 32];
+  const int tid = threadIdx.x;
+
+  for (int64_t j = blockIdx.x; j < p.N; j += gridDim.x) {
+    int64_t c0;
+    int n;
+    if (p.xp) {
+      c0 = p.xp[j];
+      n = p.xp[j + 1] - p.xp[j];
+    } else {
+      c0 = j * (int64_t)p.P;
+      n = p.P;
+    }
+    unsigned long long* keys;
+    PosT* pos;
+    if (GLOBAL_WS) {
+      keys = p.ws_keys + c0;
+      pos = reinterpret_cast<PosT*>(p.ws_pos) + c0;
+    } else {
+      keys = rsm;
+      pos = reinterpret_cast<PosT*>(rsm + p.cap);
+    }
+    if (tid == 0) s_nnan = 0;
+    __syncthreads();
+    int my_nan = 0;
+    for (int l = tid; l < n; l += RT) {
+      double v = p.xx[c0 + l];
+      unsigned long long key;
+      if (v != v) {
+        key = NAN_KEY;
+        ++my_nan;
+      } else {
+        key = key_of(p.is_signed ? fabs(v) : v);
+      }
+      keys[l] = key;
+      pos[l] = (PosT)l;
+    }
+    if (my_nan) atomicAdd(&s_nnan, my_nan);
+    __syncthreads();
+    bitonic_sort<PosT>(keys, pos, n);
+    const int nv = n - s_nnan;  // NaN sorted last
+    // zero group (dense semantics): stored zeros + implicit zeros
+    int nneg = 0, zs = 0, zimp = 0;
+    if (p.dense_sem) {
+      nneg = lower_bound(keys, nv, ZERO_KEY);
+      zs = upper_bound(keys, nv, ZERO_KEY) - nneg;
+      zimp = p.P - n;
+    }
+    const int z = zs + zimp;
+    double mymax = 0.0;
+    for (int q = tid; q < n; q += RT) {
+      const unsigned long long key = keys[q];
+      double r;
+      if (q >= nv) {
+        r = nan("");
+      } else {
+        int first, last;  // 0-based inclusive-exclusive tie run in the full column order
+        if (p.dense_sem && key == ZERO_KEY) {
+          first = nneg;
+          last = nneg + z;
+        } else {
+          first = (q > 0 && keys[q - 1] == key) ? lower_bound(keys, q, key) : q;
+          last = (q + 1 < nv && keys[q + 1] == key) ? q + 1 + upper_bound(keys + q + 1, nv - q - 1, key) : q + 1;
+          if (p.dense_sem && key > ZERO_KEY) {
+            first += zimp;
+            last += zimp;
+          }
+        }
+        r = p.ties == PLAIDGPU_TIES_AVERAGE ? 0.5 * (double)(first + 1 + last)
+            : p.ties == PLAIDGPU_TIES_MIN   ? (double)(first + 1)
+                                            : (double)last;
+        if (p.is_signed) {
+          const double v = p.xx[c0 + pos[q]];
+          r = v > 0.0 ? r : (v < 0.0 ? -r : 0.0);
+        }
+        mymax = fmax(mymax, fabs(r));
+      }
+      p.rank[c0 + pos[q]] = r;
+    }
+    double rz = 0.0;
+    if (p.dense_sem && z > 0 && !p.is_signed) {
+      rz = p.ties == PLAIDGPU_TIES_AVERAGE ? (double)nneg + 0.5 * (double)(z + 1)
+           : p.ties == PLAIDGPU_TIES_MIN   ? (double)(nneg + 1)
+                                           : (double)(nneg + z);
+      mymax = fmax(mymax, rz);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(FULL, mymax, o));
+    if ((tid & 31) == 0) s_max[tid >> 5] = mymax;
+    __syncthreads();
+    if (tid == 0) {
+      double m = 0.0;
+      for (int i = 0; i < RT / 32; ++i) m = fmax(m, s_max[i]);
+      if (p.colmax) p.colmax[j] = m;
+      if (p.r0) p.r0[j] = rz;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_expand(const int32_t* __restrict__ xp, const int32_t* __restrict__ xi,
+                                                const double* __restrict__ rank,
+                                                const double* __restrict__ r0, int32_t P, int64_t N,
+                                                double* __restrict__ dense) {
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+    double* __restrict__ d = dense + j * (int64_t)P;
+    const double fill = r0 ? r0[j] : 0.0;
+    for (int l = threadIdx.x; l < P; l += blockDim.x) d[l] = fill;
+    __syncthreads();
+    const int64_t c0 = xp[j], c1 = xp[j + 1];
+    for (int64_t e = c0 + threadIdx.x; e < c1; e += blockDim.x) d[xi[e]] = rank[e];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_xform_dense(const double* __restrict__ in, double* __restrict__ out,
+                                                     int64_t n, int mode, double a0, double a1) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = xform_value(mode, in[i], a0, a1);
+}
+
+__global__ void __launch_bounds__(256) k_max_col_nnz(const int32_t* __restrict__ xp, int64_t N, int32_t* res) {
+  int m = 0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < N;
+       j += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, xp[j + 1] - xp[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(res, m);
+}
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+template <typename PosT>
+cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_t st) {
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t per = sizeof(unsigned long long) + sizeof(PosT);
+  int cap = (max_n + 1) & ~1;  // keep the pos array 8-byte aligned behind the keys
+  if (cap < 2) cap = 2;
+  const size_t need = (size_t)cap * per;
+  cudaError_t e;
+  if (need + 2048 <= (size_t)smem_optin) {
+    p.cap = cap;
+    e = cudaFuncSetAttribute(k_rank<PosT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rank<PosT, false>, RT, need);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (grid > p.N) grid = p.N;
+    k_rank<PosT, false><<<(unsigned)grid, RT, need, st>>>(p);
+    return cudaGetLastError();
+  }
+  // column does not fit in shared memory: sort in a global workspace (slow path)
+  unsigned long long* wk = nullptr;
+  PosT* wp = nullptr;
+  e = cudaMallocAsync(&wk, (size_t)total * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMallocAsync(&wp, (size_t)total * sizeof(PosT), st);
+  if (e != cudaSuccess) return e;
+  p.ws_keys = wk;
+  p.ws_pos = wp;
+  int64_t grid = (int64_t)sm_count() * 4;
+  if (grid > p.N) grid = p.N;
+  k_rank<PosT, true><<<(unsigned)grid, RT, 0, st>>>(p);
+  e = cudaGetLastError();
+  cudaFreeAsync(wk, st);
+  cudaFreeAsync(wp, st);
+  return e;
+}
+
+}  // namespace
+
+cudaError_t launch_rank_csc(const int32_t* xp, const double* xx, int32_t P, int64_t N, int ties,
+                            int is_signed, int dense_semantics, double* rank, double* r0,
+                            double* colmax, int32_t max_col_nnz, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  RankParams p{};
+  p.xp = xp; p.xx = xx; p.P = P; p.N = N; p.ties = ties; p.is_signed = is_signed;
+  p.dense_sem = dense_semantics; p.rank = rank; p.r0 = r0; p.colmax = colmax;
+  int32_t last = 0;
+  cudaError_t e = cudaMemcpyAsync(&last, xp + N, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  if (max_col_nnz <= 65536) return launch_rank_impl<uint16_t>(p, max_col_nnz, last, st);
+  return launch_rank_impl<uint32_t>(p, max_col_nnz, last, st);
+}
+
+cudaError_t launch_rank_dense(const double* x, int32_t P, int64_t N, int ties, int is_signed,
+                              double* rank, double* colmax, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  RankParams p{};
+  p.xp = nullptr; p.xx = x; p.P = P; p.N = N; p.ties = ties; p.is_signed = is_signed;
+  p.dense_sem = 0; p.rank = rank; p.r0 = nullptr; p.colmax = colmax;
+  if (P <= 65536) return launch_rank_impl<uint16_t>(p, P, (int64_t)P * N, st);
+  return launch_rank_impl<uint32_t>(p, P, (int64_t)P * N, st);
+}
+
+cudaError_t launch_expand_ranks(const int32_t* xp, const int32_t* xi, const double* rank,
+                                const double* r0, int32_t P, int64_t N, double* dense,
+                                cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t grid = (int64_t)sm_count() * 8;
+  if (grid > N) grid = N;
+  k_expand<<<(unsigned)grid, 256, 0, st>>>(xp, xi, rank, r0, P, N, dense);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_xform_dense(const double* in, double* out, int64_t n, int mode, double a0,
+                               double a1, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  k_xform_dense<<<(unsigned)grid, 256, 0, st>>>(in, out, n, mode, a0, a1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d_res, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess || N <= 0) return e;
+  int64_t grid = (N + 255) / 256;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  k_max_col_nnz<<<(unsigned)grid, 256, 0, st>>>(xp, N, d_res);
+  return cudaGetLastError();
+}
+
+}  // namespace plaidgpu

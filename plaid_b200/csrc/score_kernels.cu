@@ -1,0 +1,175 @@
+// K1/K2 — the gene-set score product  out = t(G) %*% X  (scaled per set), the hot loop of
+// plaid() / chunked_crossprod() (reference R/plaid.R:60-87, 100-123; Matrix::crossprod ->
+// CHOLMOD ssmult/sdmult).
+//
+// Formulation (B200-first, not a translation of Gustavson-on-CPU):
+//   * scatter form: for every stored x(g, j) add it to all sets containing gene g.  Work is
+//     nnz(X) x avg-degree adds, the work-optimal count for sparse X sparse G -> dense out.
+//   * accumulators are fp64 and live in SHARED MEMORY; one warp owns one tile of Ts sets of
+//     one column at a time, so no atomics are needed: the sets of one gene are distinct, and
+//     genes are processed one after the other inside the warp.
+//   * the set axis is tiled (T tiles of Ts sets) because one fp64 column of 30k sets (240 KB)
+//     exceeds the 227 KB of shared memory; the gene -> sets adjacency is stored per X row with
+//     per-tile offsets (ptr[row][tile]) and 16-bit tile-local set ids, and is read through L1/L2
+//     (it is ~6 MB for 2.7M memberships: L2 resident).
+//   * persistent grid (a multiple of the SM count), work items (column, tile) dealt round-robin
+//     to the warps of a CTA so all warps of a CTA walk the same column at about the same time
+//     (X column and ptr sectors hit L1).
+//   * the epilogue (set scaling 1/(n_s+1e-8), scse column scaling, rank zero-group term) is
+//     fused into the flush of the tile; output is written once with coalesced streaming stores.
+#include "common.cuh"
+
+namespace plaidgpu {
+
+template <bool DENSE, bool GENERAL>
+__global__ void __launch_bounds__(256) k_score(const ScoreParams p) {
+  extern __shared__ double sacc[];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int W = blockDim.x >> 5;
+  double* __restrict__ acc = sacc + (size_t)w * p.Ts;
+  for (int l = lane; l < p.Ts; l += 32) acc[l] = 0.0;
+  __syncwarp();
+
+  const int T = p.T;
+  const int64_t ncols_cta = (p.N - blockIdx.x + gridDim.x - 1) / gridDim.x;  // columns of this CTA
+  const int64_t nitems = ncols_cta * T;
+
+  for (int64_t q = w; q < nitems; q += W) {
+    const int64_t k = q / T;
+    const int t = (int)(q - k * T);
+    const int64_t j = blockIdx.x + k * (int64_t)gridDim.x;
+
+    int64_t c0, c1;
+    if (DENSE) {
+      c0 = j * (int64_t)p.P;
+      c1 = c0 + p.P;
+    } else {
+      c0 = p.xp[j];
+      c1 = p.xp[j + 1];
+    }
+    double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
+    if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
+    double asum = 0.0;
+
+    const uint32_t* __restrict__ ptr_t = p.ptr + t;
+    const int stride = T + 1;
+    for (int64_t b = c0; b < c1; b += 32) {
+      const int64_t e = b + lane;
+      const bool valid = e < c1;
+      double xv = 0.0;
+      uint32_t q0 = 0, q1 = 0;
+      if (valid) {
+        const int gi = DENSE ? (int)(e - c0) : p.xi[e];
+        xv = p.xx[e];
+        if (GENERAL) {
+          if (p.mode >= XF_SING) {
+            xv = xform_value(p.mode, xv, p.a0, p.a1) - fb;
+          } else {
+            xv = xform_value(p.mode, xv, p.a0, p.a1);
+            asum += fabs(xv);
+          }
+        }
+        const uint32_t* pp = ptr_t + (size_t)gi * stride;
+        q0 = pp[0];
+        q1 = pp[1];
+      }
+      unsigned m = __ballot_sync(FULL, q1 > q0);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t s0 = __shfl_sync(FULL, q0, src);
+        const uint32_t s1 = __shfl_sync(FULL, q1, src);
+        const double xk = __shfl_sync(FULL, xv, src);
+        for (uint32_t ee = s0 + lane; ee < s1; ee += 32) {
+          const int l = p.idx[ee];
+          acc[l] += xk;
+        }
+        __syncwarp();  // lanes of the next gene may touch the sets just written
+      }
+    }
+
+    // ---- flush tile t of column j: fused epilogue, coalesced streaming store, re-zero ----
+    double cs = 1.0;
+    if (GENERAL && p.colnorm) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(FULL, asum, o);
+      cs = (p.colnorm == 1) ? 100.0 / (asum + 1e-8) : 1.0 / (asum / (double)p.P + 1e-8);
+    }
+    const int sbase = t * p.Ts;
+    const int tl = min(p.Ts, p.S - sbase);
+    double* __restrict__ o = p.out + j * p.ld + sbase;
+    for (int l = lane; l < tl; l += 32) {
+      double v = acc[l];
+      acc[l] = 0.0;
+      if (GENERAL) {
+        if (p.mode >= XF_SING) v += fb * p.ns[sbase + l];
+        v *= p.inv[sbase + l];
+        if (p.colnorm) v *= cs;
+      } else {
+        v *= p.inv[sbase + l];
+      }
+      __stcs(o + l, v);
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* Ts_out, int32_t* T_out,
+                            LaunchCfg* cfg) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return e;
+  const int warps = 8;
+  const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin - 1024;  // leave the 1 KB reserve
+  int32_t ts_max = (int32_t)(smem_max / (8 * warps));
+  ts_max = (ts_max / 32) * 32;
+  if (ts_max > 65536) ts_max = 65536;
+  int32_t Ts, T;
+  if (tile_hint > 0) {
+    Ts = ((tile_hint + 31) / 32) * 32;
+    if (Ts > ts_max) Ts = ts_max;
+    T = (S + Ts - 1) / Ts;
+  } else {
+    T = (S + ts_max - 1) / ts_max;
+    if (T < 1) T = 1;
+    Ts = (((S + T - 1) / T) + 31) / 32 * 32;  // even out the tiles
+    if (Ts < 32) Ts = 32;
+  }
+  cfg->warps = warps;
+  cfg->smem = (size_t)warps * Ts * sizeof(double);
+  // persistent grid: SM count x resident CTAs per SM
+  int per_sm = 0;
+  const void* fns[4] = {(const void*)k_score<false, false>, (const void*)k_score<false, true>,
+                        (const void*)k_score<true, false>, (const void*)k_score<true, true>};
+  for (int i = 0; i < 4; ++i) {
+    e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) return e;
+  }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score<false, true>, warps * 32, cfg->smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  cfg->ctas = prop.multiProcessorCount * per_sm;
+  *Ts_out = Ts;
+  *T_out = T;
+  return cudaSuccess;
+}
+
+cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st) {
+  if (p.N <= 0) return cudaSuccess;
+  const bool general = (p.mode != XF_IDENT) || p.colnorm != 0;
+  int64_t grid = cfg.ctas;
+  if (grid > p.N) grid = p.N;
+  dim3 g((unsigned)grid), b((unsigned)cfg.warps * 32);
+  if (dense) {
+    if (general) k_score<true, true><<<g, b, cfg.smem, st>>>(p);
+    else k_score<true, false><<<g, b, cfg.smem, st>>>(p);
+  } else {
+    if (general) k_score<false, true><<<g, b, cfg.smem, st>>>(p);
+    else k_score<false, false><<<g, b, cfg.smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace plaidgpu

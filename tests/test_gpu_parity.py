@@ -1,0 +1,251 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, reached through the C ABI (ctypes binding of
+include/plaidgpu.h behind plaid_b200's R-mirroring functions), against the CPU oracle on the
+same inputs.  Bars (BASELINE.json north_star): ranks bit-exact (incl. averaged ties); scores
+within 1e-6 relative — the kernels accumulate in fp64, so the tolerance asserted here is 1e-11
+(1e-9 for the pow()/exp2()-based scorers)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import plaid_b200 as pb
+from oracle import plaid_oracle as O
+from plaid_b200 import synth
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def _named(X, xr, xc, G, gr, gc):
+    return (pb.NamedMatrix(X, xr, xc), pb.NamedMatrix(G, gr, gc), O.Named(X, xr, xc), O.Named(G, gr, gc))
+
+
+# ---- the reference's own bundled fixture -----------------------------------------------------
+def test_fixture_plaid_all_variants(fixture_mats, golden, gpu_ctx):
+    Xg, Gg, _, _ = _named(*fixture_mats)
+    r = pb.plaid(Xg, Gg, ctx=gpu_ctx)
+    assert r.mat.shape == (50, 50) and r.rownames[0] == fixture_mats[5][0]
+    assert rel_err(r.mat, golden["plaid_mean_norm"]) < TOL
+    assert rel_err(pb.plaid(Xg, Gg, normalize=False, ctx=gpu_ctx).mat, golden["plaid_mean_raw"]) < TOL
+    assert rel_err(pb.plaid(Xg, Gg, stats="sum", normalize=False, ctx=gpu_ctx).mat, golden["plaid_sum_raw"]) < TOL
+
+
+def test_fixture_scorers(fixture_mats, golden, gpu_ctx):
+    Xg, Gg, _, _ = _named(*fixture_mats)
+    assert rel_err(pb.replaid_scse(Xg, Gg, ctx=gpu_ctx).mat, golden["scse_default"]) < 1e-9
+    assert rel_err(pb.replaid_scse(Xg, Gg, removeLog2=False, scoreMean=True, ctx=gpu_ctx).mat,
+                   golden["scse_mean_nolog"]) < TOL
+    assert rel_err(pb.replaid_sing(Xg, Gg, ctx=gpu_ctx).mat, golden["sing"]) < TOL
+    assert rel_err(pb.replaid_ssgsea(Xg, Gg, ctx=gpu_ctx).mat, golden["ssgsea_a0"]) < TOL
+    assert rel_err(pb.replaid_ssgsea(Xg, Gg, alpha=0.25, ctx=gpu_ctx).mat, golden["ssgsea_a025"]) < 1e-9
+    assert rel_err(pb.replaid_ucell(Xg, Gg, ctx=gpu_ctx).mat, golden["ucell"]) < TOL
+    assert rel_err(pb.replaid_aucell(Xg, Gg, ctx=gpu_ctx).mat, golden["aucell"]) < TOL
+
+
+def test_fixture_ranks_bit_exact(fixture_mats, golden, gpu_ctx):
+    X = fixture_mats[0]
+    r = pb.sparse_colranks(X, ctx=gpu_ctx)
+    assert np.array_equal(r.indices, X.indices) and np.array_equal(r.indptr, X.indptr)
+    assert np.array_equal(r.data, golden["sparse_colranks_avg"])
+    assert np.array_equal(pb.sparse_colranks(X, signed=True, ties_method="min", ctx=gpu_ctx).data,
+                          golden["sparse_colranks_min_signed"])
+    assert np.array_equal(pb.colranks(X, ctx=gpu_ctx), golden["colranks_dense_avg"])
+    assert np.array_equal(pb.colranks(X, ties_method="min", ctx=gpu_ctx), golden["colranks_dense_min"])
+
+
+# ---- synthetic configs (BASELINE.json) at sizes the oracle finishes in seconds ----------------
+@pytest.fixture(scope="module")
+def c1_like():
+    """C1: pbmc3k-shaped sparse X x hallmark-sized sets, reduced N; rows matched by NAME with
+    shuffled, partially overlapping names."""
+    P, N, S = 13714, 300, 50
+    X = synth.sparse_x_numpy(P, N, seed=synth.SEED0 + 0)
+    G = synth.genesets_numpy(4386, S, seed=synth.SEED0 + 100, size_cap=(32, 200))
+    rng = np.random.default_rng(5)
+    gnames = [f"SYM{k}" for k in range(4386)]
+    xnames = np.array(gnames + [f"OTHER{k}" for k in range(P - 4386)])
+    xnames = list(xnames[rng.permutation(P)])
+    return X, xnames, [f"c{k}" for k in range(N)], G, gnames, synth.set_names(S)
+
+
+def test_c1_plaid_sparse(c1_like, gpu_ctx):
+    Xg, Gg, Xo, Go = _named(*c1_like)
+    for stats in ["mean", "sum"]:
+        for norm in [False, True]:
+            got = pb.plaid(Xg, Gg, stats=stats, normalize=norm, ctx=gpu_ctx).mat
+            assert rel_err(got, O.plaid(Xo, Go, stats=stats, normalize=norm).mat) < TOL
+
+
+def test_multi_tile_many_sets(gpu_ctx):
+    """S large enough for several shared-memory tiles + a ragged last tile."""
+    P, N, S = 3000, 64, 9001
+    X = synth.sparse_x_numpy(P, N, seed=21)
+    G = synth.genesets_numpy(P, S, seed=22, size_cap=(5, 300))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    for norm in [False, True]:
+        assert rel_err(pb.plaid(Xg, Gg, normalize=norm, ctx=gpu_ctx).mat, O.plaid(Xo, Go, normalize=norm).mat) < TOL
+    info = gpu_ctx.plan_info()
+    assert info["n_tiles"] >= 3 and info["n_tiles"] * info["tile_sets"] >= S
+
+
+def test_c2_dense_bulk(gpu_ctx):
+    P, N, S = 2000, 48, 3000
+    X = synth.dense_x_numpy(P, N, seed=synth.SEED0 + 1)
+    G = synth.genesets_numpy(P, S, seed=synth.SEED0 + 101, size_cap=(5, 500))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    assert rel_err(pb.plaid(Xg, Gg, ctx=gpu_ctx).mat, O.plaid(Xo, Go).mat) < TOL
+    assert rel_err(pb.plaid(Xg, Gg, stats="sum", normalize=False, ctx=gpu_ctx).mat,
+                   O.plaid(Xo, Go, stats="sum", normalize=False).mat) < TOL
+
+
+def test_c3_rank_scorers_sparse(gpu_ctx):
+    P, N, S = 4000, 96, 700
+    X = synth.sparse_x_numpy(P, N, seed=synth.SEED0 + 2)
+    G = synth.genesets_numpy(P, S, seed=synth.SEED0 + 102, size_cap=(5, 400))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    assert rel_err(pb.replaid_ssgsea(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_ssgsea(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_sing(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_sing(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_ucell(Xg, Gg, rmax=300, ctx=gpu_ctx).mat, O.replaid_ucell(Xo, Go, rmax=300).mat) < TOL
+    assert rel_err(pb.replaid_aucell(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_aucell(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_scse(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_scse(Xo, Go).mat) < 1e-9
+
+
+def test_rank_scorers_dense_input(gpu_ctx):
+    P, N, S = 1500, 20, 200
+    X = synth.dense_x_numpy(P, N, seed=31)
+    X[::9] = np.round(X[::9])  # ties
+    G = synth.genesets_numpy(P, S, seed=32, size_cap=(5, 200))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    assert rel_err(pb.replaid_sing(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_sing(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_ssgsea(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_ssgsea(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_ucell(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_ucell(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_aucell(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_aucell(Xo, Go).mat) < TOL
+    assert rel_err(pb.replaid_scse(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_scse(Xo, Go).mat) < 1e-9
+
+
+# ---- ranking: bit-exact, adversarial -----------------------------------------------------------
+@pytest.mark.parametrize("ties", ["average", "min", "max"])
+@pytest.mark.parametrize("signed", [False, True])
+def test_colranks_bit_exact(ties, signed, gpu_ctx):
+    P, N = 700, 40
+    X = synth.sparse_x_numpy(P, N, seed=41, density=0.15).tolil()
+    X[:, 3] = 0  # empty column
+    X[:5, 4] = 1.25  # all-tied column
+    X = sp.csc_matrix(X)
+    X.data[::5] *= -1.0
+    X.data[::13] = 0.0  # explicit stored zeros
+    X.data[7] = -0.0
+    got = pb.sparse_colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx)
+    assert np.array_equal(got.data, O.sparse_colranks(X, signed=signed, ties_method=ties).data)
+    assert np.array_equal(pb.colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx),
+                          O.colranks(X, signed=signed, ties_method=ties))
+    D = X.toarray()
+    assert np.array_equal(pb.colranks(D, signed=signed, ties_method=ties, ctx=gpu_ctx),
+                          O.colranks(D, signed=signed, ties_method=ties))
+
+
+def test_colranks_nan_and_large_column(gpu_ctx):
+    rng = np.random.default_rng(9)
+    D = np.round(rng.normal(size=(20000, 3)), 1)  # bulk-sized column (P = 20k), heavy ties
+    D[5, 0] = np.nan
+    got = pb.colranks(D, ctx=gpu_ctx)
+    want = O.colranks(D)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+
+
+# ---- normalize_medians ---------------------------------------------------------------------------
+def test_normalize_medians_edge_cases(gpu_ctx):
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(501, 33))
+    assert rel_err(pb.normalize_medians(x, ctx=gpu_ctx), O.normalize_medians(x)) < 1e-13
+    y = np.abs(x)
+    y[rng.random(y.shape) < 0.4] = 0.0
+    y[:, 2] = 0.0  # all-zero column -> median NA -> 0
+    y[:, 3] = 7.0  # constant column: every radix digit is tied
+    y[10, 5] = np.nan
+    assert rel_err(pb.normalize_medians(y, ctx=gpu_ctx), O.normalize_medians(y)) < 1e-13
+    for iz in [False, True]:
+        assert rel_err(pb.normalize_medians(y, ignore_zero=iz, ctx=gpu_ctx), O.normalize_medians(y, ignore_zero=iz)) < 1e-13
+    z = rng.normal(size=(4000, 5)) * 10.0 ** rng.integers(-200, 200, size=(4000, 5))  # wild exponents
+    assert rel_err(pb.normalize_medians(z, ctx=gpu_ctx), O.normalize_medians(z)) < 1e-13
+    e = rng.normal(size=(64, 2))  # even count: mean of the two middles
+    assert rel_err(pb.normalize_medians(e, ctx=gpu_ctx), O.normalize_medians(e)) < 1e-13
+
+
+# ---- reference edge cases ------------------------------------------------------------------------
+def test_no_overlap_returns_none(gpu_ctx):
+    X = synth.sparse_x_numpy(50, 4, seed=1, density=0.3)
+    G = synth.genesets_numpy(50, 5, seed=2, size_cap=(3, 10))
+    assert pb.plaid(pb.NamedMatrix(X, [f"a{k}" for k in range(50)]), pb.NamedMatrix(G, [f"b{k}" for k in range(50)]),
+                    ctx=gpu_ctx) is None
+
+
+def test_vector_input_single_sample_and_empty_set(gpu_ctx):
+    P, S = 200, 10
+    G = synth.genesets_numpy(P, S, seed=3, size_cap=(3, 20)).tolil()
+    G[:, 4] = 0  # empty gene set -> score 0
+    G = sp.csc_matrix(G)
+    names = synth.gene_names(P)
+    v = np.random.default_rng(6).normal(size=P)
+    got = pb.plaid(pb.NamedMatrix(v, names), pb.NamedMatrix(G, names), normalize=False, ctx=gpu_ctx).mat
+    want = O.plaid(O.Named(v, names), O.Named(G, names), normalize=False).mat
+    assert got.shape == (S, 1) and got[4, 0] == 0.0
+    assert rel_err(got, want) < TOL
+
+
+def test_nan_propagates_only_to_sets_with_that_gene(gpu_ctx):
+    P, N, S = 300, 6, 40
+    X = synth.sparse_x_numpy(P, N, seed=51, density=0.3)
+    X.data[3] = np.nan
+    G = synth.genesets_numpy(P, S, seed=52, size_cap=(3, 40))
+    names = synth.gene_names(P)
+    got = pb.plaid(pb.NamedMatrix(X, names), pb.NamedMatrix(G, names), normalize=False, ctx=gpu_ctx).mat
+    want = O.plaid(O.Named(X, names), O.Named(G, names), normalize=False).mat
+    assert np.isnan(want).any() and not np.isnan(want).all()
+    assert rel_err(got, want) < TOL
+
+
+def test_chunked_crossprod_matches(gpu_ctx):
+    X = synth.sparse_x_numpy(500, 30, seed=61, density=0.2)
+    G = synth.genesets_numpy(500, 70, seed=62, size_cap=(3, 60))
+    Gs = G @ sp.diags(1.0 / (1e-8 + np.asarray(G.sum(0)).ravel()))
+    assert rel_err(pb.chunked_crossprod(Gs, X, ctx=gpu_ctx), O.chunked_crossprod(sp.csc_matrix(Gs), X)) < TOL
+    assert rel_err(pb.chunked_crossprod(G, X, chunk=7, ctx=gpu_ctx), O.chunked_crossprod(G, X, chunk=7)) < TOL
+
+
+# ---- size-independent properties at larger sizes (no oracle needed) ---------------------------------
+def test_properties_linearity_and_column_independence(gpu_ctx):
+    P, N, S = 20000, 512, 30000
+    X = synth.sparse_x_numpy(P, N, seed=71)
+    G = synth.genesets_numpy(P, 2000, seed=72)
+    G = sp.hstack([G] * 15).tocsc()[:, :S]  # 30k sets (repeated blocks), several tiles
+    names = synth.gene_names(P)
+    Gn = pb.NamedMatrix(G, names)
+    a = pb.plaid(pb.NamedMatrix(X, names), Gn, stats="sum", normalize=False, ctx=gpu_ctx).mat
+    assert a.shape == (S, N)
+    # repeated set blocks give identical rows
+    assert np.array_equal(a[:2000], a[2000:4000])
+    # column independence: scoring a column subset gives the same bits (sharding invariant)
+    sub = pb.plaid(pb.NamedMatrix(X[:, 100:228], names), Gn, stats="sum", normalize=False, ctx=gpu_ctx).mat
+    assert np.array_equal(sub, a[:, 100:228])
+    # linearity in X (power-of-two scaling is exact in fp64)
+    b = pb.plaid(pb.NamedMatrix(X * 4.0, names), Gn, stats="sum", normalize=False, ctx=gpu_ctx).mat
+    assert np.array_equal(b, 4.0 * a)
+    # sum of all set scores == sum over genes of x * degree (checksum of checksums)
+    deg = np.asarray(G.sum(1)).ravel()
+    chk = np.asarray(X.T @ deg).ravel()
+    assert np.allclose(a.sum(0), chk, rtol=1e-12)
+    # median-normalised output: every column has the same median (mean of medians), zeros ignored
+    n = pb.plaid(pb.NamedMatrix(X, names), Gn, ctx=gpu_ctx).mat
+    raw = pb.plaid(pb.NamedMatrix(X, names), Gn, normalize=False, ctx=gpu_ctx).mat
+    z = raw.copy()
+    z[z == 0] = np.nan
+    med = np.nanmedian(z, axis=0)
+    assert np.allclose(n, raw - med[None, :] + med.mean(), rtol=0, atol=1e-12)
