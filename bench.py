@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — plaid() cells x genesets scored per second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU reference arm (oracle port)
+
+Workload (named in `config.workload`): BASELINE.json configs[3] — plaid() on a 1M-cell x 20k-gene
+sparse single-cell matrix with 30k gene sets, sample-sharded over 8 B200 — run as its per-GPU
+shard: 125,000 cells per GPU ("weak" scaling: N GPUs score N x 125,000 cells; N = 8 is C4 exactly).
+One step = one full plaid(X, matG) (stats="mean", normalize=TRUE: score product + median
+normalisation) over the rank's shard.
+
+  value      whole-job cells x genesets / s with X (CSC) and the S x N output resident in HBM;
+  e2e        the same call through the public plaid_b200.plaid API / C ABI with HOST (pinned)
+             buffers: H2D of the CSC shard and D2H of the S x N result inside the timed region;
+  roofline   dominant kernel (k_score): algorithmic bytes of SURVEY.md §8(d) per launch / CUDA-event
+             duration of that launch (events on the library's own stream), vs MEASURED_PEAKS.json;
+  cpu_baseline  the oracle (numpy/scipy restatement of the R path) on 1 host core, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_GENES, S_SETS, CELLS_PER_GPU = 20000, 30000, 125000
+METRIC = "plaid() cells x genesets scored/sec"
+UNIT = "cells*genesets/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
+    ap.add_argument("--e2e-cells", type=int, default=32768, help="cells per GPU of the host-buffer e2e leg (0 = skip)")
+    ap.add_argument("--cpu-cells", type=int, default=3000, help="cells of the 1-core CPU baseline sample (0 = skip)")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(dev, rank, n_cells):
+    """Synthetic C4-shaped inputs generated on the GPU: same G on every rank, X shard seeded per rank."""
+    import scipy.sparse as sp
+    from plaid_b200 import synth
+    Gp, Gi = synth.genesets_torch(P_GENES, S_SETS, seed=synth.SEED0 + 3, device=dev)
+    G = sp.csc_matrix((np.ones(Gi.size), Gi, Gp), shape=(P_GENES, S_SETS))
+    p, i, x = synth.sparse_x_torch(P_GENES, n_cells, seed=synth.SEED0 + 3 + 1000 * (rank + 1), device=dev)
+    return G, p, i, x
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import plaid_b200 as pb
+    from plaid_b200 import _lib as L, sharded, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+        comm = sharded.TorchComm(device=dev)
+    else:
+        dist = None
+        comm = sharded.LocalComm()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Nc = a.cells_per_gpu
+    G, xp, xi, xx = make_inputs(dev, rank, Nc)
+    nnz = int(xx.numel())
+    names = synth.gene_names(P_GENES)
+    rowmap = pb.make_rowmap(names, names)
+    ctx = pb.Context(local)
+    ctx.set_genesets(G)
+    lib = ctx.lib
+    out = torch.empty(S_SETS * Nc, dtype=torch.float64, device=dev)
+    keep: list = []
+    from plaid_b200.api import _matrix_struct, _opts
+    M = _matrix_struct(pb.DeviceCSC(xp, xi, xx, (P_GENES, Nc)), keep)
+    opts = _opts(lib, scorer=L.PLAID, stats_mean=1, normalize=1, out_location=L.DEVICE)
+
+    def step():
+        return sharded.score_shard(ctx, comm, M, rowmap, opts, out.data_ptr(), Nc)
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    lib.plaidgpu_reset_launch_count(ctx.h)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    k_ms = np.zeros(4)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+        k_ms += [ctx.kernel_ms(k) for k in range(4)]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count()
+    tt = torch.tensor([dt, float(launches), k_ms[0], float(nnz)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt, launches, score_ms_sum, nnz_tot = float(mx[0]), int(sm[1]), float(mx[2]), float(sm[3])
+    else:
+        score_ms_sum, nnz_tot = float(k_ms[0]), float(nnz)
+    value = S_SETS * float(Nc) * world * a.steps / dt
+
+    # ---- roofline of the dominant kernel (k_score): SURVEY §8(d) algorithmic bytes per launch -------
+    nnzG = int(G.nnz)
+    alg_bytes = nnz * 12 + (Nc + 1) * 4 + nnzG * 4 + (S_SETS + 1) * 4 + S_SETS * Nc * 8
+    score_ms = score_ms_sum / a.steps
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (score_ms * 1e-3) / 1e9
+    traffic = None
+    tnote = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as fh:
+            tj = json.load(fh)
+        traffic = float(tj["dram_bytes_per_cell"]) * Nc
+        tnote = tj.get("note")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_score", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": tnote, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 3),
+                "kernel_share_of_step": round(score_ms / (dt / a.steps * 1e3), 3),
+                "ms_per_step_by_kernel": {"score": round(k_ms[0] / a.steps, 3), "colstats": round(k_ms[1] / a.steps, 3),
+                                          "fixup": round(k_ms[2] / a.steps, 3)},
+                "plan": ctx.plan_info()}
+
+    # ---- e2e: public API, HOST pinned buffers, H2D + D2H inside the timed region ---------------------
+    e2e = None
+    if a.e2e_cells > 0:
+        Ne = min(a.e2e_cells, Nc)
+        hp = torch.empty(Ne + 1, dtype=torch.int32).pin_memory()
+        hp.copy_(xp[:Ne + 1])
+        ne = int(hp[Ne])
+        hi = torch.empty(ne, dtype=torch.int32).pin_memory(); hi.copy_(xi[:ne])
+        hx = torch.empty(ne, dtype=torch.float64).pin_memory(); hx.copy_(xx[:ne])
+        hout = torch.empty(S_SETS * Ne, dtype=torch.float64).pin_memory()
+        Mh = L.Matrix()
+        Mh.kind, Mh.location, Mh.P, Mh.N = L.CSC, L.HOST, P_GENES, Ne
+        Mh.p, Mh.i, Mh.x = hp.data_ptr(), hi.data_ptr(), hx.data_ptr()
+        oh = _opts(lib, scorer=L.PLAID, stats_mean=1, normalize=1, out_location=L.HOST)
+
+        def estep():
+            return sharded.score_shard(ctx, comm, Mh, rowmap, oh, hout.data_ptr(), Ne)
+
+        estep()
+        barrier()
+        ke = max(1, min(a.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            estep()
+            _ = float(hout[0])  # the result is read on the host
+        barrier()
+        edt = time.perf_counter() - t0
+        et = torch.tensor([edt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        e2e = {"value": S_SETS * float(Ne) * world * ke / float(et[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int((Ne + 1) * 4 + ne * 12) * world, "d2h_bytes_per_step": int(S_SETS * Ne * 8) * world,
+               "cells_per_gpu": Ne, "steps": ke, "ms_per_step": round(float(et[0]) / ke * 1e3, 2),
+               "note": "host buffers pinned; same plaid() path incl. normalisation; sample of the shard's first cells"}
+        del hout, hx, hi
+
+    # ---- CPU baseline: oracle port, 1 core, bounded sample (rank 0, N = 1 only) -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_cells > 0:
+        cpu = cpu_baseline(G, xp, xi, xx, min(a.cpu_cells, Nc), names)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4-shard plaid(): sparse dgCMatrix {P_GENES} genes x {Nc} cells/GPU (~7% nnz, "
+                                       f"pbmc3k-shaped), {S_SETS} MSigDB-scale gene sets, stats=mean, normalize=TRUE; "
+                                       f"C4 (1M cells) = 8 such shards",
+                           "genes": P_GENES, "cells_per_gpu": Nc, "cells_total": Nc * world, "gene_sets": S_SETS,
+                           "nnz_x_per_gpu": nnz, "nnz_g": nnzG, "sharding": f"columns x{world}, no data-path collective",
+                           "l2": "inputs_exceed_l2 (X 2.1 GB + out 30 GB per GPU vs 126 MB L2; no flush needed)",
+                           "timing": "K steps bracketed by barrier + cuda synchronize, max over ranks"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(G, xp, xi, xx, n, names):
+    """Oracle plaid() (scipy Gustavson product + densify + median normalisation) on ONE core."""
+    import scipy.sparse as sp
+    from oracle import plaid_oracle as O
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    hp = xp[:n + 1].cpu().numpy()
+    ne = int(hp[-1])
+    X = sp.csc_matrix((xx[:ne].cpu().numpy(), xi[:ne].cpu().numpy(), hp), shape=(P_GENES, n))
+    Xn, Gn = O.Named(X, names, None), O.Named(G, names, None)
+    t0 = time.perf_counter()
+    if threadpool_limits:
+        with threadpool_limits(limits=1):
+            r = O.plaid(Xn, Gn)
+    else:
+        r = O.plaid(Xn, Gn)
+    dt = time.perf_counter() - t0
+    res = {"value": S_SETS * float(n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"first {n} cells of the shard x all {S_SETS} sets, oracle/plaid_oracle.plaid (numpy/scipy restatement "
+                     f"of R/plaid.R; R itself is not installable here), {dt:.1f} s",
+           "seconds": round(dt, 2)}
+    del r
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _w_init(Gd, Gi, Gp, names):
+    import scipy.sparse as sp
+    _W["G"] = sp.csc_matrix((Gd, Gi, Gp), shape=(P_GENES, S_SETS))
+    _W["names"] = names
+
+
+def _w_phase1(args):
+    """raw scores of one column block + its medians (kept in the worker like R keeps gsetX)"""
+    import scipy.sparse as sp
+    from oracle import plaid_oracle as O
+    d, i, p, n = args
+    X = sp.csc_matrix((d, i, p), shape=(P_GENES, n))
+    raw = O.plaid(O.Named(X, _W["names"], None), O.Named(_W["G"], _W["names"], None), normalize=False).mat
+    z = raw.copy()
+    z[raw == 0] = np.nan
+    med_nz = np.nan_to_num(O.col_medians_narm(z))
+    med_all = O.col_medians_narm(raw)
+    _W["raw"], _W["ma"], _W["mz"] = raw, med_all, med_nz
+    return float(np.nanmin(raw)), med_all, med_nz
+
+
+def _w_phase2(args):
+    use_nz, c = args
+    raw = _W.pop("raw")
+    med = _W.pop("mz") if use_nz else _W.pop("ma")
+    out = (raw - med[None, :]) + c  # sweep(x, 2, medx, '-') + mean(medx)   (R/plaid.R:572)
+    return float(out[0, 0])
+
+
+def run_reference(a):
+    """Reference arm: the reference's CPU algorithm (oracle port of R/plaid.R — R is not installed
+    here, so the reference itself cannot be compiled/run) on all host cores, column-sharded."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import torch
+    from oracle import plaid_oracle as O
+    from plaid_b200 import synth
+    cores = os.cpu_count() or 1
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"  # data generation only
+    per_core = 400
+    n = per_core * cores
+    G, xp, xi, xx = make_inputs(dev, 0, n)
+    names = synth.gene_names(P_GENES)
+    hp = xp.cpu().numpy(); hi = xi.cpu().numpy(); hx = xx.cpu().numpy()
+    blocks = []
+    for w in range(cores):
+        lo, hi_ = w * per_core, (w + 1) * per_core
+        e0, e1 = int(hp[lo]), int(hp[hi_])
+        blocks.append((hx[e0:e1], hi[e0:e1], (hp[lo:hi_ + 1] - e0).astype(np.int32), per_core))
+    os.environ["OMP_NUM_THREADS"] = "1"
+    ctxm = mp.get_context("fork")
+    with ctxm.Pool(cores, initializer=_w_init, initargs=(G.data, G.indices, G.indptr, names)) as pool:
+        def step():
+            res = pool.map(_w_phase1, blocks, chunksize=1)
+            smin = min(r[0] for r in res)
+            use_nz = smin == 0
+            med = np.concatenate([r[2] if use_nz else r[1] for r in res])
+            c = O.r_mean(med)
+            pool.map(_w_phase2, [(use_nz, c)] * cores, chunksize=1)
+        for _ in range(a.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step()
+        dt = time.perf_counter() - t0
+    v = S_SETS * float(n) * a.steps / dt
+    sample = (f"{n} cells ({per_core}/core) x {S_SETS} sets per step; oracle port of R/plaid.R (scipy Gustavson product, "
+              f"densify, per-column medians, sweep), column-sharded over {cores} processes")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4-shard plaid(): sparse dgCMatrix {P_GENES} genes x cells (~7% nnz), {S_SETS} gene sets, "
+                                   f"stats=mean, normalize=TRUE", "genes": P_GENES, "gene_sets": S_SETS,
+                       "cells_per_step": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
