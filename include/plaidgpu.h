@@ -201,9 +201,11 @@ void plaidgpu_reset_launch_count(plaidgpu_ctx* ctx);
 double plaidgpu_last_kernel_ms(const plaidgpu_ctx* ctx, int which);
 /* cudaStream_t of the context, as void* (so callers can order their own work) */
 void* plaidgpu_stream(const plaidgpu_ctx* ctx);
-/* plan facts after a score call: tile size, tile count, mapped memberships, adds per column */
+/* plan facts after a score call: scatter tile size / count, mapped memberships, launch shape, and the
+ * gather blocks (genes per block, number of blocks; 0 blocks = scatter only) */
 int plaidgpu_plan_info(const plaidgpu_ctx* ctx, int32_t* tile_sets, int32_t* n_tiles,
-                       int64_t* nnz_mapped, int32_t* warps_per_cta, int32_t* ctas);
+                       int64_t* nnz_mapped, int32_t* warps_per_cta, int32_t* ctas,
+                       int32_t* gather_block, int32_t* gather_blocks);
 
 #ifdef __cplusplus
 }

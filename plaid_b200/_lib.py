@@ -61,7 +61,8 @@ SYMBOLS = {
     "plaidgpu_last_kernel_ms": (C.c_double, [C.c_void_p, C.c_int]),
     "plaidgpu_stream": (C.c_void_p, [C.c_void_p]),
     "plaidgpu_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
-                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -121,11 +121,12 @@ class Context:
         return float(self.lib.plaidgpu_last_kernel_ms(self.h, which))
 
     def plan_info(self) -> dict:
-        ts, nt, wp, ct = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        ts, nt, wp, ct, gk, gb = (C.c_int32() for _ in range(6))
         nm = C.c_int64()
-        self.check(self.lib.plaidgpu_plan_info(self.h, C.byref(ts), C.byref(nt), C.byref(nm), C.byref(wp), C.byref(ct)))
-        return {"tile_sets": ts.value, "n_tiles": nt.value, "nnz_mapped": nm.value,
-                "warps_per_cta": wp.value, "ctas": ct.value}
+        self.check(self.lib.plaidgpu_plan_info(self.h, C.byref(ts), C.byref(nt), C.byref(nm), C.byref(wp), C.byref(ct),
+                                               C.byref(gk), C.byref(gb)))
+        return {"tile_sets": ts.value, "n_tiles": nt.value, "nnz_mapped": nm.value, "warps_per_cta": wp.value,
+                "ctas": ct.value, "gather_block": gk.value, "gather_blocks": gb.value}
 
 
 _default_ctx: dict = {}

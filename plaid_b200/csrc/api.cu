@@ -64,6 +64,12 @@ struct plaidgpu_ctx {
   int64_t nnz_mapped = 0;
   int32_t n_overlap = 0;
   DevBuf d_ptr, d_idx, d_inv_mean, d_inv_one, d_ns, d_custom_inv, d_beta;
+  // gather blocks: sparse X -> one block of the K highest-degree rows (d_dmap) + scatter for the rest;
+  // dense X -> every row, in nblocks blocks of K consecutive rows, no scatter at all
+  bool plan_dense = false;
+  int32_t gK = 0, gblocks = 0;
+  int64_t g_entries = 0;
+  DevBuf d_dmap, d_dptr, d_didx, d_colscale;
 
   // current scoring call
   bool in_call = false, computed = false;
@@ -99,8 +105,8 @@ int fail_cuda(plaidgpu_ctx* c, cudaError_t e, const char* where) {
   } while (0)
 
 // ---- plan ------------------------------------------------------------------------------
-int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_hint) {
-  if (c->plan_ok && c->plan_P == P && c->plan_hint == tile_hint &&
+int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_hint, bool dense) {
+  if (c->plan_ok && c->plan_P == P && c->plan_hint == tile_hint && c->plan_dense == dense &&
       memcmp(c->plan_rowmap.data(), rowmap, sizeof(int32_t) * (size_t)P) == 0)
     return PLAIDGPU_OK;
   c->plan_ok = false;
@@ -122,61 +128,154 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   cudaError_t e = score_configure(c->device, S, tile_hint, &Ts, &T, &c->cfg);
   if (e != cudaSuccess) return fail_cuda(c, e, "score_configure");
 
-  // CSR by X row; walking the sets in ascending order leaves every row's list sorted by set
-  std::vector<uint32_t> rowcnt((size_t)P + 1, 0);
+  // degrees of the X rows and set sizes n_s = |set s ∩ rows(X)|
+  std::vector<uint32_t> deg((size_t)P, 0);
   std::vector<double> ns((size_t)S, 0.0);
+  int64_t nnzm = 0;
   for (int32_t s = 0; s < S; ++s)
     for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
       const int32_t r = g2x[c->Gi[q]];
       if (r >= 0) {
-        ++rowcnt[r + 1];
+        ++deg[r];
         ns[s] += 1.0;
+        ++nnzm;
       }
     }
-  for (int32_t r = 0; r < P; ++r) rowcnt[r + 1] += rowcnt[r];
-  const int64_t nnzm = rowcnt[P];
-  std::vector<uint32_t> fill(rowcnt.begin(), rowcnt.end() - 1);
-  std::vector<uint16_t> idx((size_t)std::max<int64_t>(nnzm, 1));
-  std::vector<uint32_t> ptr((size_t)P * (T + 1));
-  std::vector<int32_t> setof((size_t)std::max<int64_t>(nnzm, 1));
-  for (int32_t s = 0; s < S; ++s)
-    for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
-      const int32_t r = g2x[c->Gi[q]];
-      if (r >= 0) setof[fill[r]++] = s;
+
+  // ---- gather blocks ---------------------------------------------------------------------
+  const int Kmax = gather_max_block(c->device);
+  std::vector<uint16_t> dmap;          // sparse mode: row -> local id in the block, 0xFFFF otherwise
+  std::vector<int32_t> blk_of_row;     // row -> block (dense mode) / 0 or -1 (sparse mode)
+  int32_t gK = 0, gblocks = 0;
+  if (dense) {
+    gK = std::min<int32_t>(Kmax, ((P + 31) / 32) * 32);
+    if (gK <= 0) return fail(c, PLAIDGPU_ERR_CUDA, "no shared memory for the gather tile");
+    gblocks = (P + gK - 1) / gK;
+  } else if (Kmax > 0 && S >= 1024 && nnzm >= 100000) {
+    // the K highest-degree rows: in single-cell data these are the ubiquitous genes, i.e. the rows
+    // of X that are nearly dense and carry most of the adds
+    std::vector<int32_t> order((size_t)P);
+    for (int32_t r = 0; r < P; ++r) order[r] = r;
+    const int32_t want = std::min<int32_t>(Kmax, P);
+    std::partial_sort(order.begin(), order.begin() + want, order.end(),
+                      [&](int32_t x, int32_t y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
+    int32_t k = 0;
+    while (k < want && deg[order[k]] > 0) ++k;
+    gK = ((k + 31) / 32) * 32;
+    if (gK > Kmax) gK = Kmax;
+    if (k > gK) k = gK;
+    if (k >= 32) {
+      dmap.assign((size_t)P, 0xFFFFu);
+      std::vector<int32_t> sel(order.begin(), order.begin() + k);
+      std::sort(sel.begin(), sel.end());  // local ids ascend with the row index (reference sum order)
+      for (int32_t i = 0; i < k; ++i) dmap[sel[i]] = (uint16_t)i;
+      gblocks = 1;
+    } else {
+      gK = 0;
     }
-  for (int32_t r = 0; r < P; ++r) {
-    uint32_t e0 = rowcnt[r];
-    const uint32_t e1 = rowcnt[r + 1];
-    uint32_t* pr = ptr.data() + (size_t)r * (T + 1);
-    for (int32_t t = 0; t < T; ++t) {
-      pr[t] = e0;
-      const int32_t hi = (t + 1) * Ts;
-      while (e0 < e1 && setof[e0] < hi) {
-        idx[e0] = (uint16_t)(setof[e0] - t * Ts);
-        ++e0;
+  }
+  // set-major member lists per block, 16-bit local ids, padded to multiples of 4 with gK (a zero row)
+  std::vector<uint32_t> dptr;
+  std::vector<uint16_t> didx;
+  if (gblocks > 0) {
+    dptr.assign((size_t)gblocks * (S + 1), 0);
+    // count
+    std::vector<uint32_t> cnt((size_t)gblocks * S, 0);
+    for (int32_t s = 0; s < S; ++s)
+      for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+        const int32_t r = g2x[c->Gi[q]];
+        if (r < 0) continue;
+        if (dense) ++cnt[(size_t)(r / gK) * S + s];
+        else if (dmap[r] != 0xFFFFu) ++cnt[s];
       }
+    uint64_t off = 0;
+    for (int32_t b = 0; b < gblocks; ++b) {
+      for (int32_t s = 0; s < S; ++s) {
+        dptr[(size_t)b * (S + 1) + s] = (uint32_t)off;
+        off += (cnt[(size_t)b * S + s] + 3u) & ~3u;
+      }
+      dptr[(size_t)b * (S + 1) + S] = (uint32_t)off;
     }
-    pr[T] = e1;
+    if (off >= 0xFFFFFFFFull) return fail(c, PLAIDGPU_ERR_ARG, "gene-set matrix too large for 32-bit offsets");
+    didx.assign((size_t)std::max<uint64_t>(off, 4), (uint16_t)gK);
+    std::vector<uint32_t> pos((size_t)gblocks * S);
+    for (int32_t b = 0; b < gblocks; ++b)
+      for (int32_t s = 0; s < S; ++s) pos[(size_t)b * S + s] = dptr[(size_t)b * (S + 1) + s];
+    // members of a set arrive in the order of matG's rows; sort each list so sums run in ascending X row
+    for (int32_t s = 0; s < S; ++s)
+      for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+        const int32_t r = g2x[c->Gi[q]];
+        if (r < 0) continue;
+        if (dense) didx[pos[(size_t)(r / gK) * S + s]++] = (uint16_t)(r % gK);
+        else if (dmap[r] != 0xFFFFu) didx[pos[s]++] = dmap[r];
+      }
+    for (int32_t b = 0; b < gblocks; ++b)
+      for (int32_t s = 0; s < S; ++s) {
+        const uint32_t lo = dptr[(size_t)b * (S + 1) + s];
+        std::sort(didx.begin() + lo, didx.begin() + pos[(size_t)b * S + s]);
+      }
+    c->g_entries = (int64_t)off;
+  }
+
+  // ---- scatter adjacency (sparse X only): CSR by X row without the gather-block rows ----------
+  std::vector<uint32_t> ptr;
+  std::vector<uint16_t> idx(1);
+  int64_t nnz_scatter = 0;
+  if (!dense) {
+    auto in_block = [&](int32_t r) { return !dmap.empty() && dmap[r] != 0xFFFFu; };
+    std::vector<uint32_t> rowcnt((size_t)P + 1, 0);
+    for (int32_t r = 0; r < P; ++r) rowcnt[r + 1] = rowcnt[r] + (in_block(r) ? 0u : deg[r]);
+    nnz_scatter = rowcnt[P];
+    std::vector<uint32_t> fill(rowcnt.begin(), rowcnt.end() - 1);
+    std::vector<int32_t> setof((size_t)std::max<int64_t>(nnz_scatter, 1));
+    // walking the sets in ascending order leaves every row's list sorted by set
+    for (int32_t s = 0; s < S; ++s)
+      for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+        const int32_t r = g2x[c->Gi[q]];
+        if (r >= 0 && !in_block(r)) setof[fill[r]++] = s;
+      }
+    idx.assign((size_t)std::max<int64_t>(nnz_scatter, 1), 0);
+    ptr.assign((size_t)P * (T + 1), 0);
+    for (int32_t r = 0; r < P; ++r) {
+      uint32_t e0 = rowcnt[r];
+      const uint32_t e1 = rowcnt[r + 1];
+      uint32_t* pr = ptr.data() + (size_t)r * (T + 1);
+      for (int32_t t = 0; t < T; ++t) {
+        pr[t] = e0;
+        const int32_t hi = (t + 1) * Ts;
+        while (e0 < e1 && setof[e0] < hi) {
+          idx[e0] = (uint16_t)(setof[e0] - t * Ts);
+          ++e0;
+        }
+      }
+      pr[T] = e1;
+    }
   }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
   for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76
 
-  CK(c->d_ptr.reserve(ptr.size() * sizeof(uint32_t)));
-  CK(c->d_idx.reserve(idx.size() * sizeof(uint16_t)));
-  CK(c->d_inv_mean.reserve((size_t)S * sizeof(double)));
-  CK(c->d_inv_one.reserve((size_t)S * sizeof(double)));
-  CK(c->d_ns.reserve((size_t)S * sizeof(double)));
-  CK(cudaMemcpyAsync(c->d_ptr.p, ptr.data(), ptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_inv_mean.p, inv_mean.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_inv_one.p, inv_one.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_ns.p, ns.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e2 = b.reserve(std::max<size_t>(bytes, 16));
+    if (e2 != cudaSuccess || bytes == 0) return e2;
+    return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream);
+  };
+  CK(up(c->d_ptr, ptr.data(), ptr.size() * sizeof(uint32_t)));
+  CK(up(c->d_idx, idx.data(), idx.size() * sizeof(uint16_t)));
+  CK(up(c->d_inv_mean, inv_mean.data(), (size_t)S * sizeof(double)));
+  CK(up(c->d_inv_one, inv_one.data(), (size_t)S * sizeof(double)));
+  CK(up(c->d_ns, ns.data(), (size_t)S * sizeof(double)));
+  CK(up(c->d_dmap, dmap.data(), dmap.size() * sizeof(uint16_t)));
+  CK(up(c->d_dptr, dptr.data(), dptr.size() * sizeof(uint32_t)));
+  CK(up(c->d_didx, didx.data(), didx.size() * sizeof(uint16_t)));
   CK(cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
   c->Ts = Ts;
   c->T = T;
+  c->gK = gK;
+  c->gblocks = gblocks;
   c->nnz_mapped = nnzm;
   c->plan_P = P;
   c->plan_hint = tile_hint;
+  c->plan_dense = dense;
   c->plan_rowmap.assign(rowmap, rowmap + P);
   c->plan_ok = true;
   return PLAIDGPU_OK;
@@ -325,7 +424,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
-                    &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
+                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
                     &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -344,13 +443,15 @@ double plaidgpu_last_kernel_ms(const plaidgpu_ctx* c, int which) {
 void* plaidgpu_stream(const plaidgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int plaidgpu_plan_info(const plaidgpu_ctx* c, int32_t* tile_sets, int32_t* n_tiles, int64_t* nnz_mapped,
-                       int32_t* warps_per_cta, int32_t* ctas) {
+                       int32_t* warps_per_cta, int32_t* ctas, int32_t* gather_block, int32_t* gather_blocks) {
   if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
   if (tile_sets) *tile_sets = c->Ts;
   if (n_tiles) *n_tiles = c->T;
   if (nnz_mapped) *nnz_mapped = c->nnz_mapped;
   if (warps_per_cta) *warps_per_cta = c->cfg.warps;
   if (ctas) *ctas = c->cfg.ctas;
+  if (gather_block) *gather_block = c->gK;
+  if (gather_blocks) *gather_blocks = c->gblocks;
   return PLAIDGPU_OK;
 }
 
@@ -393,7 +494,7 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   if (opts->scorer < PLAIDGPU_PLAID || opts->scorer > PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
   if (opts->scorer == PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva is not available in this build");
   if (opts->scorer == PLAIDGPU_SSGSEA && !(1.0 + opts->alpha > 0.0)) return fail(c, PLAIDGPU_ERR_ARG, "ssgsea needs alpha > -1");
-  int rc = build_plan(c, X->P, rowmap, opts->tile_sets);
+  int rc = build_plan(c, X->P, rowmap, opts->tile_sets, X->kind == PLAIDGPU_DENSE);
   if (rc) return rc;
   rc = load_matrix(c, X);
   if (rc) return rc;
@@ -475,8 +576,11 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   p.Ts = c->Ts;
   p.mode = XF_IDENT;
   p.a0 = p.a1 = 0.0;
-  p.colnorm = 0;
+  p.colscale = nullptr;
+  p.accumulate = 0;
+  p.final = 1;
   p.ld = c->S;
+  int colnorm = 0;
   bool mean = true;
   c->need_norm = false;
   switch (o.scorer) {
@@ -488,7 +592,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       const bool rl = o.remove_log2 < 0 ? (scal->x_min == 0.0 && scal->x_max < 20.0) : (o.remove_log2 != 0);
       if (rl) p.mode = c->dense ? XF_EXP2_POS : XF_EXP2;
       mean = o.score_mean != 0;
-      p.colnorm = o.score_mean ? 2 : 1;
+      colnorm = o.score_mean ? 2 : 1;
       break;
     }
     case PLAIDGPU_SING:
@@ -540,9 +644,48 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   }
   p.out = c->raw;
 
+  if (colnorm) {  // replaid.scse: column sums / means of |X| over ALL rows of X (R/plaid.R:176,181)
+    CK(c->d_colscale.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    CK(launch_colabs(c->xp, c->xx, c->P, c->N, p.mode, p.a0, p.a1, colnorm, c->d_colscale.as<double>(), c->stream));
+    c->launches += 1;
+    p.colscale = c->d_colscale.as<double>();
+  }
+
   CK(cudaEventRecord(c->ev[0], c->stream));
-  CK(launch_score(p, c->dense, c->cfg, c->stream));
-  c->launches += 1;
+  if (c->gblocks > 0) {
+    GatherParams g{};
+    g.xp = c->xp;
+    g.xi = c->xi;
+    g.xx = p.xx;
+    g.r0 = p.r0;
+    g.P = c->P;
+    g.N = c->N;
+    g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>();
+    g.K = c->gK;
+    g.didx = c->d_didx.as<uint16_t>();
+    g.inv = p.inv;
+    g.ns = p.ns;
+    g.colscale = p.colscale;
+    g.S = c->S;
+    g.mode = p.mode;
+    g.a0 = p.a0;
+    g.a1 = p.a1;
+    g.out = c->raw;
+    g.ld = c->S;
+    for (int32_t b = 0; b < c->gblocks; ++b) {
+      g.g0 = b * c->gK;
+      g.dptr = c->d_dptr.as<uint32_t>() + (size_t)b * (c->S + 1);
+      g.accumulate = b > 0;
+      g.final = c->dense && (b == c->gblocks - 1);  // sparse X: the scatter pass finishes the scores
+      CK(launch_gather(g, c->stream));
+      c->launches += 1;
+    }
+    p.accumulate = 1;
+  }
+  if (!c->dense) {
+    CK(launch_score(p, false, c->cfg, c->stream));
+    c->launches += 1;
+  }
   CK(cudaEventRecord(c->ev[1], c->stream));
 
   scal->score_min = INFINITY;

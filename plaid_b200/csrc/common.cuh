@@ -41,9 +41,39 @@ struct ScoreParams {
   // transform
   int32_t mode;
   double a0, a1;
-  // scse column normalisation: 0 none, 1 = 100/(sum|x|+1e-8), 2 = 1/(mean|x|+1e-8)
-  int32_t colnorm;
+  // per-column scale applied in the epilogue (replaid.scse), or nullptr
+  const double* colscale;
+  // accumulate != 0: add to what `out` already holds (partial sums of an earlier pass);
+  // final != 0: apply the epilogue (set scale, zero-group term, column scale); else store raw sums
+  int32_t accumulate, final;
   // output, column-major S x N, leading dimension ld
+  double* out;
+  int64_t ld;
+};
+
+// Gather pass over one block of K genes (the dense-ish part of the product):
+//   out[s, j] (+)= sum over members g of set s inside the block of X[g, j]
+// with the block's X rows staged DENSE in shared memory for 32 columns at a time and one warp
+// per set (lanes = columns), accumulating in registers.
+struct GatherParams {
+  const int32_t* xp;     // CSC (sparse mode) or nullptr (dense mode)
+  const int32_t* xi;
+  const double* xx;
+  const double* r0;      // rank scorers: zero-group rank per column, else nullptr
+  int32_t P;
+  int64_t N;
+  const uint16_t* dmap;  // sparse mode: X row -> local id in the block, 0xFFFF = not in block
+  int32_t g0;            // dense mode: block = rows [g0, g0 + K)
+  int32_t K;
+  const uint32_t* dptr;  // [S + 1] offsets into didx (multiples of 4)
+  const uint16_t* didx;  // local gene ids, each set's list padded to a multiple of 4 with K (a zero row)
+  const double* inv;
+  const double* ns;
+  const double* colscale;
+  int32_t S;
+  int32_t mode;
+  double a0, a1;
+  int32_t accumulate, final;
   double* out;
   int64_t ld;
 };
@@ -58,6 +88,13 @@ struct LaunchCfg {
 cudaError_t score_configure(int device, int32_t S, int32_t tile_sets_hint, int32_t* Ts, int32_t* T,
                             LaunchCfg* cfg);
 cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st);
+
+// gather_kernels.cu
+int gather_max_block(int device);  // largest K (genes per block) the shared-memory tile allows
+cudaError_t launch_gather(const GatherParams& p, cudaStream_t st);
+// colscale[j] = 100 / (sum_i |f(x_ij)| + 1e-8) (kind 1) or 1 / (mean_i |f(x_ij)| + 1e-8) (kind 2)
+cudaError_t launch_colabs(const int32_t* xp, const double* xx, int32_t P, int64_t N, int mode, double a0,
+                          double a1, int kind, double* colscale, cudaStream_t st);
 
 // stats_kernels.cu
 // per-column statistics of a dense S x N matrix (ld = leading dimension):
@@ -110,6 +147,16 @@ __device__ __forceinline__ double xform_value(int mode, double v, double a0, dou
     case XF_AUCELL: return 1.08 * fmax((v - (a0 - a1)) / a1, 0.0);
     default: return v;
   }
+}
+
+// epilogue shared by the scatter and gather kernels: raw set sum -> score
+__device__ __forceinline__ double score_epilogue(double v, int s, int64_t j, double fb, int mode,
+                                                 const double* __restrict__ inv, const double* __restrict__ ns,
+                                                 const double* __restrict__ colscale) {
+  if (mode >= XF_SING) v += fb * ns[s];
+  v *= inv[s];
+  if (colscale) v *= colscale[j];
+  return v;
 }
 
 // order-preserving 64-bit key of a double; -0 and +0 share one key

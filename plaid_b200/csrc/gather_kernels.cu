@@ -1,0 +1,174 @@
+// K2 — gather pass of the gene-set score product over one BLOCK of genes whose rows of X are
+// (nearly) dense: the ubiquitous genes of a single-cell matrix (a few hundred genes carry most of
+// the adds because they are expressed in most cells AND sit in thousands of sets), or every gene
+// of a dense bulk / proteomics matrix (reference R/plaid.R:100-123 with a dense y -> cholmod_sdmult).
+//
+// For such rows the scatter form (score_kernels.cu) is bound by shared-memory read-modify-write
+// (16 B per add, bank conflicts, one gene in flight per accumulator tile).  Here the block's X rows
+// are staged DENSE in shared memory for 32 columns at a time ([K+1][32] fp64, row K = zeros), one
+// warp owns one set at a time, lanes = columns: every member of the set costs ONE conflict-free
+// LDS.64 (256 contiguous bytes) and a register DADD.  The set -> member lists of the block are
+// 16-bit local gene ids, padded to multiples of 4 so a warp fetches 4 members with one 8-byte
+// broadcast load.  32 finished sets x 32 columns are transposed through a padded shared-memory
+// tile so that the global stores are 256-byte contiguous runs along the set axis of the
+// column-major output.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+namespace plaidgpu {
+
+namespace {
+
+constexpr int GC = 32;   // columns per CTA batch = lanes
+constexpr int GW = 8;    // warps per CTA
+constexpr int GS = 32;   // sets per staging tile
+constexpr int GPAD = 33;
+
+__global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
+  extern __shared__ double gsm[];
+  double* __restrict__ Xs = gsm;                                   // [(K + 1)][GC]
+  double* __restrict__ st = gsm + (size_t)(p.K + 1) * GC;          // [GW][GC][GPAD]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double* __restrict__ stw = st + (size_t)w * GC * GPAD;
+  const int K = p.K;
+  const int64_t nbatch = (p.N + GC - 1) / GC;
+
+  for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+    const int64_t j0 = bt * GC;
+    const int nc = (int)min((int64_t)GC, p.N - j0);
+    // ---- stage the block's rows of X for these columns ---------------------------------
+    if (p.xp) {
+      for (int i = tid; i < (K + 1) * GC / 2; i += GW * 32) reinterpret_cast<double2*>(Xs)[i] = make_double2(0.0, 0.0);
+      __syncthreads();
+      for (int c = w; c < nc; c += GW) {
+        const int64_t j = j0 + c;
+        const int64_t c0 = p.xp[j], c1 = p.xp[j + 1];
+        double fb = 0.0;
+        if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
+        for (int64_t e = c0 + lane; e < c1; e += 32) {
+          const unsigned d = p.dmap[p.xi[e]];
+          if (d != 0xFFFFu) {
+            double v = xform_value(p.mode, p.xx[e], p.a0, p.a1);
+            if (p.mode >= XF_SING) v -= fb;
+            Xs[d * GC + c] = v;
+          }
+        }
+      }
+    } else {
+      // dense mode: rows [g0, g0 + K) of a column-major P x N matrix; rows beyond P and row K are zero
+      for (int c = w; c < GC; c += GW) {
+        const int64_t j = j0 + c;
+        const double* __restrict__ col = p.xx + j * (int64_t)p.P + p.g0;
+        const int rows = (c < nc) ? min(K, p.P - p.g0) : 0;
+        for (int r = lane; r <= K; r += 32) Xs[r * GC + c] = (r < rows) ? xform_value(p.mode, col[r], p.a0, p.a1) : 0.0;
+      }
+    }
+    __syncthreads();
+
+    // ---- gather: one warp per set, lanes = columns -----------------------------------------
+    for (int s0 = w * GS; s0 < p.S; s0 += GW * GS) {
+      const int ns = min(GS, p.S - s0);
+      for (int i = 0; i < ns; ++i) {
+        const uint32_t b = p.dptr[s0 + i], e = p.dptr[s0 + i + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const ushort4* __restrict__ ids = reinterpret_cast<const ushort4*>(p.didx + b);
+        const int n4 = (int)((e - b) >> 2);
+#pragma unroll 2
+        for (int m = 0; m < n4; ++m) {
+          const ushort4 q = __ldg(ids + m);
+          a0 += Xs[q.x * GC + lane];
+          a1 += Xs[q.y * GC + lane];
+          a2 += Xs[q.z * GC + lane];
+          a3 += Xs[q.w * GC + lane];
+        }
+        stw[lane * GPAD + i] = (a0 + a1) + (a2 + a3);
+      }
+      __syncwarp();
+      // transposed write-out: for each column 32 consecutive sets (256 contiguous bytes)
+      const bool live = lane < ns;
+      const int s = s0 + lane;
+      for (int c = 0; c < nc; ++c) {
+        if (live) {
+          const int64_t j = j0 + c;
+          double* __restrict__ o = p.out + j * p.ld + s;
+          double v = stw[c * GPAD + lane];
+          if (p.accumulate) v += __ldcs(o);
+          if (p.final) {
+            double fb = 0.0;
+            if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
+            v = score_epilogue(v, s, j, fb, p.mode, p.inv, p.ns, p.colscale);
+          }
+          __stcs(o, v);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();  // Xs is rebuilt by the next batch
+  }
+}
+
+// one warp per column: sum of |f(x)| over the column's stored entries (sparse) or P rows (dense)
+__global__ void __launch_bounds__(256) k_colabs(const int32_t* __restrict__ xp, const double* __restrict__ xx,
+                                                int32_t P, int64_t N, int mode, double a0, double a1, int kind,
+                                                double* __restrict__ colscale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = w0; j < N; j += nw) {
+    const int64_t c0 = xp ? xp[j] : j * (int64_t)P;
+    const int64_t c1 = xp ? xp[j + 1] : c0 + P;
+    double a = 0.0;
+    for (int64_t e = c0 + lane; e < c1; e += 32) a += fabs(xform_value(mode, xx[e], a0, a1));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
+    if (lane == 0) colscale[j] = (kind == 1) ? 100.0 / (a + 1e-8) : 1.0 / (a / (double)P + 1e-8);
+  }
+}
+
+size_t gather_smem(int K) { return ((size_t)(K + 1) * GC + (size_t)GW * GC * GPAD) * sizeof(double); }
+
+}  // namespace
+
+int gather_max_block(int device) {
+  int optin = 0;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+  const size_t fixed = (size_t)GW * GC * GPAD * sizeof(double) + 1024;
+  if ((size_t)optin <= fixed) return 0;
+  int K = (int)(((size_t)optin - fixed) / (GC * sizeof(double))) - 1;
+  K = (K / 32) * 32;
+  if (const char* e = getenv("PLAIDGPU_GATHER_K")) {  // tuning knob (bench / profiling only)
+    const int v = atoi(e);
+    if (v >= 0 && v < K) K = (v / 32) * 32;
+  }
+  return K > 0xFFF0 ? 0xFFF0 : K;
+}
+
+cudaError_t launch_gather(const GatherParams& p, cudaStream_t st) {
+  if (p.N <= 0 || p.K <= 0) return cudaSuccess;
+  const size_t smem = gather_smem(p.K);
+  cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather, GW * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sms * per_sm;
+  const int64_t nbatch = (p.N + GC - 1) / GC;
+  if (grid > nbatch) grid = nbatch;
+  k_gather<<<(unsigned)grid, GW * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colabs(const int32_t* xp, const double* xx, int32_t P, int64_t N, int mode, double a0,
+                          double a1, int kind, double* colscale, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t grid = (N + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_colabs<<<(unsigned)grid, 256, 0, st>>>(xp, xx, P, N, mode, a0, a1, kind, colscale);
+  return cudaGetLastError();
+}
+
+}  // namespace plaidgpu

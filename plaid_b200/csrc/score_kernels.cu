@@ -54,8 +54,6 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreParams p) {
     }
     double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
     if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
-    double asum = 0.0;
-
     const uint32_t* __restrict__ ptr_t = p.ptr + t;
     const int stride = T + 1;
     // Software pipeline over batches of 32 stored entries:
@@ -104,7 +102,6 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreParams p) {
           xv = (b + lane < c1) ? xform_value(p.mode, xv, p.a0, p.a1) - fb : 0.0;
         } else {
           xv = (b + lane < c1) ? xform_value(p.mode, xv, p.a0, p.a1) : 0.0;
-          asum += fabs(xv);
         }
       }
       if (__ballot_sync(FULL, len_c != 0) != 0) {  // else: no gene of this batch is in a set of this tile
@@ -166,25 +163,14 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreParams p) {
     }
 
     // ---- flush tile t of column j: fused epilogue, coalesced streaming store, re-zero ----
-    double cs = 1.0;
-    if (GENERAL && p.colnorm) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(FULL, asum, o);
-      cs = (p.colnorm == 1) ? 100.0 / (asum + 1e-8) : 1.0 / (asum / (double)p.P + 1e-8);
-    }
     const int sbase = t * p.Ts;
     const int tl = min(p.Ts, p.S - sbase);
     double* __restrict__ o = p.out + j * p.ld + sbase;
     for (int l = lane; l < tl; l += 32) {
       double v = acc[l];
       acc[l] = 0.0;
-      if (GENERAL) {
-        if (p.mode >= XF_SING) v += fb * p.ns[sbase + l];
-        v *= p.inv[sbase + l];
-        if (p.colnorm) v *= cs;
-      } else {
-        v *= p.inv[sbase + l];
-      }
+      if (p.accumulate) v += __ldcs(o + l);  // partial sums of the gather pass
+      if (p.final) v = score_epilogue(v, sbase + l, j, fb, GENERAL ? p.mode : XF_IDENT, p.inv, p.ns, p.colscale);
       __stcs(o + l, v);
     }
     __syncwarp();
@@ -238,7 +224,7 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
 
 cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st) {
   if (p.N <= 0) return cudaSuccess;
-  const bool general = (p.mode != XF_IDENT) || p.colnorm != 0;
+  const bool general = (p.mode != XF_IDENT);
   int64_t grid = cfg.ctas;
   if (grid > p.N) grid = p.N;
   dim3 g((unsigned)grid), b((unsigned)cfg.warps * 32);
