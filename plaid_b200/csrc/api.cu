@@ -176,7 +176,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   }
   // set-major member lists per block, 16-bit local ids, padded to multiples of 4 with gK (a zero row)
   std::vector<uint32_t> dptr;
-  std::vector<uint16_t> didx;
+  std::vector<uint32_t> didx;  // local id * 256 = byte offset of the row in the [K+1][32] fp64 tile
   if (gblocks > 0) {
     dptr.assign((size_t)gblocks * (S + 1), 0);
     // count
@@ -197,7 +197,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
       dptr[(size_t)b * (S + 1) + S] = (uint32_t)off;
     }
     if (off >= 0xFFFFFFFFull) return fail(c, PLAIDGPU_ERR_ARG, "gene-set matrix too large for 32-bit offsets");
-    didx.assign((size_t)std::max<uint64_t>(off, 4), (uint16_t)gK);
+    didx.assign((size_t)std::max<uint64_t>(off, 4), (uint32_t)gK * 256u);
     std::vector<uint32_t> pos((size_t)gblocks * S);
     for (int32_t b = 0; b < gblocks; ++b)
       for (int32_t s = 0; s < S; ++s) pos[(size_t)b * S + s] = dptr[(size_t)b * (S + 1) + s];
@@ -206,8 +206,8 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
       for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
         const int32_t r = g2x[c->Gi[q]];
         if (r < 0) continue;
-        if (dense) didx[pos[(size_t)(r / gK) * S + s]++] = (uint16_t)(r % gK);
-        else if (dmap[r] != 0xFFFFu) didx[pos[s]++] = dmap[r];
+        if (dense) didx[pos[(size_t)(r / gK) * S + s]++] = (uint32_t)(r % gK) * 256u;
+        else if (dmap[r] != 0xFFFFu) didx[pos[s]++] = (uint32_t)dmap[r] * 256u;
       }
     for (int32_t b = 0; b < gblocks; ++b)
       for (int32_t s = 0; s < S; ++s) {
@@ -234,22 +234,27 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         const int32_t r = g2x[c->Gi[q]];
         if (r >= 0 && !in_block(r)) setof[fill[r]++] = s;
       }
-    idx.assign((size_t)std::max<int64_t>(nnz_scatter, 1), 0);
+    // per (row, tile) lists of 16-bit byte offsets (tile-local set id * 8), each padded to a multiple
+    // of 4 entries with 0xFFFF so that a lane always reads whole 8-byte chunks
+    idx.clear();
+    idx.reserve((size_t)nnz_scatter + (size_t)nnz_scatter / 4 + 16);
     ptr.assign((size_t)P * (T + 1), 0);
     for (int32_t r = 0; r < P; ++r) {
       uint32_t e0 = rowcnt[r];
       const uint32_t e1 = rowcnt[r + 1];
       uint32_t* pr = ptr.data() + (size_t)r * (T + 1);
       for (int32_t t = 0; t < T; ++t) {
-        pr[t] = e0;
+        pr[t] = (uint32_t)idx.size();
         const int32_t hi = (t + 1) * Ts;
         while (e0 < e1 && setof[e0] < hi) {
-          idx[e0] = (uint16_t)(setof[e0] - t * Ts);
+          idx.push_back((uint16_t)((setof[e0] - t * Ts) * 8));
           ++e0;
         }
+        while (idx.size() & 3) idx.push_back((uint16_t)0xFFFFu);
       }
-      pr[T] = e1;
+      pr[T] = (uint32_t)idx.size();
     }
+    for (int k = 0; k < 8; ++k) idx.push_back((uint16_t)0xFFFFu);  // chunk prefetch may read one chunk past a list
   }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
   for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76
@@ -266,7 +271,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   CK(up(c->d_ns, ns.data(), (size_t)S * sizeof(double)));
   CK(up(c->d_dmap, dmap.data(), dmap.size() * sizeof(uint16_t)));
   CK(up(c->d_dptr, dptr.data(), dptr.size() * sizeof(uint32_t)));
-  CK(up(c->d_didx, didx.data(), didx.size() * sizeof(uint16_t)));
+  CK(up(c->d_didx, didx.data(), didx.size() * sizeof(uint32_t)));
   CK(cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
   c->Ts = Ts;
   c->T = T;
@@ -662,7 +667,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     g.N = c->N;
     g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>();
     g.K = c->gK;
-    g.didx = c->d_didx.as<uint16_t>();
+    g.didx = c->d_didx.as<uint32_t>();
     g.inv = p.inv;
     g.ns = p.ns;
     g.colscale = p.colscale;

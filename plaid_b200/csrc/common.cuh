@@ -66,7 +66,8 @@ struct GatherParams {
   int32_t g0;            // dense mode: block = rows [g0, g0 + K)
   int32_t K;
   const uint32_t* dptr;  // [S + 1] offsets into didx (multiples of 4)
-  const uint16_t* didx;  // local gene ids, each set's list padded to a multiple of 4 with K (a zero row)
+  const uint32_t* didx;  // byte offsets (local id * 256) of the members' rows in the shared-memory tile; each
+                         // set's list is padded to a multiple of 4 with row K (zeros)
   const double* inv;
   const double* ns;
   const double* colscale;

@@ -21,9 +21,9 @@ namespace plaidgpu {
 namespace {
 
 constexpr int GC = 32;   // columns per CTA batch = lanes
-constexpr int GW = 8;    // warps per CTA
-constexpr int GS = 32;   // sets per staging tile
-constexpr int GPAD = 33;
+constexpr int GW = 16;   // warps per CTA
+constexpr int GS = 8;    // sets per staging tile
+constexpr int GPAD = 9;
 
 __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
   extern __shared__ double gsm[];
@@ -67,32 +67,33 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
     __syncthreads();
 
     // ---- gather: one warp per set, lanes = columns -----------------------------------------
+    const char* __restrict__ xlane = reinterpret_cast<const char*>(Xs) + lane * 8;
     for (int s0 = w * GS; s0 < p.S; s0 += GW * GS) {
       const int ns = min(GS, p.S - s0);
       for (int i = 0; i < ns; ++i) {
         const uint32_t b = p.dptr[s0 + i], e = p.dptr[s0 + i + 1];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const ushort4* __restrict__ ids = reinterpret_cast<const ushort4*>(p.didx + b);
+        const uint4* __restrict__ ids = reinterpret_cast<const uint4*>(p.didx + b);  // byte offsets of rows
         const int n4 = (int)((e - b) >> 2);
 #pragma unroll 2
         for (int m = 0; m < n4; ++m) {
-          const ushort4 q = __ldg(ids + m);
-          a0 += Xs[q.x * GC + lane];
-          a1 += Xs[q.y * GC + lane];
-          a2 += Xs[q.z * GC + lane];
-          a3 += Xs[q.w * GC + lane];
+          const uint4 q = __ldg(ids + m);
+          a0 += *reinterpret_cast<const double*>(xlane + q.x);
+          a1 += *reinterpret_cast<const double*>(xlane + q.y);
+          a2 += *reinterpret_cast<const double*>(xlane + q.z);
+          a3 += *reinterpret_cast<const double*>(xlane + q.w);
         }
         stw[lane * GPAD + i] = (a0 + a1) + (a2 + a3);
       }
       __syncwarp();
-      // transposed write-out: for each column 32 consecutive sets (256 contiguous bytes)
-      const bool live = lane < ns;
-      const int s = s0 + lane;
-      for (int c = 0; c < nc; ++c) {
-        if (live) {
+      // transposed write-out: 4 columns x 8 consecutive sets (64 contiguous bytes each) per store
+      const int si = lane & 7, cg = lane >> 3;
+      if (si < ns) {
+        const int s = s0 + si;
+        for (int c = cg; c < nc; c += 4) {
           const int64_t j = j0 + c;
           double* __restrict__ o = p.out + j * p.ld + s;
-          double v = stw[c * GPAD + lane];
+          double v = stw[c * GPAD + si];
           if (p.accumulate) v += __ldcs(o);
           if (p.final) {
             double fb = 0.0;

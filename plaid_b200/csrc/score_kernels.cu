@@ -6,8 +6,7 @@
 //   * scatter form: for every stored x(g, j) add it to all sets containing gene g.  Work is
 //     nnz(X) x avg-degree adds, the work-optimal count for sparse X sparse G -> dense out.
 //   * accumulators are fp64 and live in SHARED MEMORY; one warp owns one tile of Ts sets of
-//     one column at a time, so no atomics are needed: the sets of one gene are distinct, and
-//     genes are processed one after the other inside the warp.
+//     one column at a time (no other warp touches it), lanes = genes (see k_scatter).
 //   * the set axis is tiled (T tiles of Ts sets) because one fp64 column of 30k sets (240 KB)
 //     exceeds the 227 KB of shared memory; the gene -> sets adjacency is stored per X row with
 //     per-tile offsets (ptr[row][tile]) and 16-bit tile-local set ids, and is read through L1/L2
@@ -23,19 +22,44 @@
 
 namespace plaidgpu {
 
-template <bool DENSE, bool GENERAL>
-__global__ void __launch_bounds__(256, 1) k_score(const ScoreParams p) {
+// One warp owns one accumulator tile (Ts sets of one column) at a time.  LANES = GENES: every lane
+// streams the tile-local set list of ONE stored entry (gene) of the column, one set per step, so 32
+// read-modify-writes of 32 different genes are in flight per step no matter how short the individual
+// lists are.  Two lanes may hit the same set in the same step (two genes of one set): each lane
+// first writes its lane id into a per-set byte tag and only the lane that reads its own id back does
+// the read-modify-write; the others retry (about one step in seven needs a second round).
+//
+// Work distribution inside the warp is a queue: a batch of 32 entries of the column is staged in
+// shared memory (list range, value, first 8-byte chunk of the list; empty lists are dropped), a lane
+// that finished its list takes the next record.  Batches are prepared three rotations ahead in
+// registers (entry -> row pointers -> first chunk), so no global-load latency sits on the refill
+// path.  Lists are padded to multiples of 4 entries (0xFFFF): all lanes cross chunk boundaries
+// together and refills happen only there.
+struct __align__(16) GeneRec {
+  uint32_t cur, end;
+  double x;
+  uint2 chunk;   // entries [cur, cur + 4)
+  uint2 chunk1;  // entries [cur + 4, cur + 8) (garbage when the list is shorter; never used then)
+};
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const int W = blockDim.x >> 5;
+  const int tagw = (p.Ts + 15) & ~15;
   double* __restrict__ acc = sacc + (size_t)w * p.Ts;
-  uint2* gq = reinterpret_cast<uint2*>(sacc + (size_t)W * p.Ts) + w * 32;
-  double* gx = sacc + (size_t)W * p.Ts + W * 32 + w * 32;
+  char* __restrict__ accb = reinterpret_cast<char*>(acc);
+  unsigned char* __restrict__ tag = reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) + (size_t)w * tagw;
+  GeneRec* __restrict__ rec = reinterpret_cast<GeneRec*>(reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) +
+                                                         (size_t)W * tagw) + w * 32;
   for (int l = lane; l < p.Ts; l += 32) acc[l] = 0.0;
   __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
 
   const int T = p.T;
+  const int stride = T + 1;
   const int64_t ncols_cta = (p.N - blockIdx.x + gridDim.x - 1) / gridDim.x;  // columns of this CTA
   const int64_t nitems = ncols_cta * T;
 
@@ -43,135 +67,154 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreParams p) {
     const int64_t k = q / T;
     const int t = (int)(q - k * T);
     const int64_t j = blockIdx.x + k * (int64_t)gridDim.x;
-
-    int64_t c0, c1;
-    if (DENSE) {
-      c0 = j * (int64_t)p.P;
-      c1 = c0 + p.P;
-    } else {
-      c0 = p.xp[j];
-      c1 = p.xp[j + 1];
-    }
+    const int64_t c0 = p.xp[j], c1 = p.xp[j + 1];
     double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
     if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
     const uint32_t* __restrict__ ptr_t = p.ptr + t;
-    const int stride = T + 1;
-    // Software pipeline over batches of 32 stored entries:
-    //   stage 0 (two batches ahead): row index + value of the entry        (coalesced)
-    //   stage 1 (one batch ahead)  : ptr[row][t], ptr[row][t+1]            (gather, L1/L2)
-    //   stage 2 (current)          : set lists, 8 genes at a time, the next 8 lists' first
-    //                                chunks already in flight while 8 are accumulated
-    int gi_n = 0;            // batch b+1 after the rotate below: row indices
-    double xv_n = 0.0;
-    uint32_t q0_c = 0, len_c = 0;
-    double xv_c = 0.0;
-    auto load_entry = [&](int64_t e, int& gi, double& xv) {
-      gi = -1;
-      xv = 0.0;
-      if (e < c1) {
-        gi = DENSE ? (int)(e - c0) : p.xi[e];
-        xv = p.xx[e];
-      }
-    };
-    auto load_ptr = [&](int gi, uint32_t& q0, uint32_t& len) {
-      q0 = 0;
-      len = 0;
-      if (gi >= 0) {
-        const uint32_t* pp = ptr_t + (size_t)gi * stride;
-        q0 = pp[0];
-        len = pp[1] - q0;
-      }
-    };
-    {
-      int gi0;
-      load_entry(c0 + lane, gi0, xv_c);
-      load_ptr(gi0, q0_c, len_c);
-      load_entry(c0 + 32 + lane, gi_n, xv_n);
-    }
-    for (int64_t b = c0; b < c1; b += 32) {
-      // rotate the pipeline: issue the loads of the next batches before touching this one
-      uint32_t q0_n, len_n;
-      load_ptr(gi_n, q0_n, len_n);
-      int gi_nn;
-      double xv_nn;
-      load_entry(b + 64 + lane, gi_nn, xv_nn);
 
-      double xv = xv_c;
-      if (GENERAL) {
-        if (p.mode >= XF_SING) {
-          xv = (b + lane < c1) ? xform_value(p.mode, xv, p.a0, p.a1) - fb : 0.0;
-        } else {
-          xv = (b + lane < c1) ? xform_value(p.mode, xv, p.a0, p.a1) : 0.0;
-        }
+    // ---- batch pipeline (lane i prepares entry i of a batch) ---------------------------------
+    int64_t ebase = c0;          // first entry of the batch whose (row, value) load is issued next
+    int gi1 = -1;                // R1: row index + value loaded
+    double x1 = 0.0;
+    uint32_t cur2 = 0, end2 = 0; // R2: row pointers loaded
+    double x2 = 0.0;
+    uint32_t cur3 = 0, end3 = 0; // R3: first chunk loaded -> ready to be staged
+    double x3 = 0.0;
+    uint2 ch3 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), ch3b = ch3;
+    int qhead = 0, qcount = 0;   // staged batch: records [qhead, qcount) are unassigned (warp-uniform)
+
+    // one rotation: stage R3 into shared memory, R2 -> R3 (+chunk load), R1 -> R2 (+pointer loads),
+    // issue the (row, value) loads of the next batch
+    auto rotate = [&]() {
+      const bool have = cur3 < end3;
+      const unsigned m = __ballot_sync(FULL, have);
+      if (have) {
+        GeneRec r;
+        r.cur = cur3; r.end = end3; r.x = x3; r.chunk = ch3; r.chunk1 = ch3b;
+        rec[__popc(m & lt)] = r;
       }
-      if (__ballot_sync(FULL, len_c != 0) != 0) {  // else: no gene of this batch is in a set of this tile
-        gq[lane] = make_uint2(q0_c, len_c);
-        gx[lane] = xv;
+      qhead = 0;
+      qcount = __popc(m);
+      __syncwarp();
+      cur3 = cur2; end3 = end2; x3 = x2;
+      if (cur3 < end3) {
+        ch3 = *reinterpret_cast<const uint2*>(p.idx + cur3);
+        ch3b = *reinterpret_cast<const uint2*>(p.idx + cur3 + 4);
+      }
+      cur2 = 0; end2 = 0;
+      if (gi1 >= 0) {
+        const uint32_t* pp = ptr_t + (size_t)gi1 * stride;
+        cur2 = pp[0];
+        end2 = pp[1];
+        x2 = x1;
+        if (GENERAL) x2 = xform_value(p.mode, x1, p.a0, p.a1) - (p.mode >= XF_SING ? fb : 0.0);
+      }
+      gi1 = -1;
+      if (ebase + lane < c1) {
+        gi1 = p.xi[ebase + lane];
+        x1 = p.xx[ebase + lane];
+      }
+      ebase += 32;
+    };
+    // prime: after three rotations the first batch is in R3; the fourth stages it
+    rotate();
+    rotate();
+    rotate();
+    int remaining = (int)((c1 - c0 + 31) >> 5);  // batches still to be staged (one per further rotation)
+    uint32_t cur = 0, end = 0;   // this lane's active list
+    double x = 0.0;
+    uint2 buf = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), nbuf = buf, nnbuf = buf;
+
+    for (;;) {
+      // ---- chunk boundary (every 4 steps, all lanes together): advance chunk / take a new gene ----
+      bool need = cur >= end;
+      if (!need) {
+        buf = nbuf;
+        nbuf = nnbuf;
+      }
+      for (;;) {
+        const unsigned nm = __ballot_sync(FULL, need);
+        if (nm == 0) break;
+        if (qhead >= qcount) {
+          if (remaining == 0) break;
+          rotate();
+          --remaining;
+          continue;
+        }
+        const int pos = qhead + __popc(nm & lt);
+        if (need && pos < qcount) {
+          const GeneRec r = rec[pos];
+          cur = r.cur; end = r.end; x = r.x; buf = r.chunk; nbuf = r.chunk1;
+          need = false;
+        }
+        qhead += __popc(nm);
         __syncwarp();
-        int lk[8], ln[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint2 g = gq[k];
-          lk[k] = (lane < (int)g.y) ? (int)p.idx[g.x + lane] : -1;
-        }
-#pragma unroll 1
-        for (int k0 = 0; k0 < 32; k0 += 8) {
-          if (k0 + 8 < 32) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint2 g = gq[k0 + 8 + k];
-              ln[k] = (lane < (int)g.y) ? (int)p.idx[g.x + lane] : -1;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const double xk = gx[k0 + k];
-            if (lk[k] >= 0) acc[lk[k]] += xk;
-            __syncwarp();  // the next gene may hit a set this one just updated
-            const uint2 g = gq[k0 + k];
-            if (g.y > 32) {  // warp-uniform: long list, remaining chunks 4 at a time (distinct sets)
-              const uint32_t s1 = g.x + g.y;
-              for (uint32_t eb = g.x + 32; eb < s1; eb += 128) {
-                const uint32_t ee = eb + lane;
-                const int l0 = (ee < s1) ? (int)p.idx[ee] : -1;
-                const int l1 = (ee + 32 < s1) ? (int)p.idx[ee + 32] : -1;
-                const int l2 = (ee + 64 < s1) ? (int)p.idx[ee + 64] : -1;
-                const int l3 = (ee + 96 < s1) ? (int)p.idx[ee + 96] : -1;
-                double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                if (l0 >= 0) v0 = acc[l0];
-                if (l1 >= 0) v1 = acc[l1];
-                if (l2 >= 0) v2 = acc[l2];
-                if (l3 >= 0) v3 = acc[l3];
-                if (l0 >= 0) acc[l0] = v0 + xk;
-                if (l1 >= 0) acc[l1] = v1 + xk;
-                if (l2 >= 0) acc[l2] = v2 + xk;
-                if (l3 >= 0) acc[l3] = v3 + xk;
-              }
-              __syncwarp();
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) lk[k] = ln[k];
-        }
-        __syncwarp();  // gq / gx are rewritten by the next batch
       }
-      q0_c = q0_n;
-      len_c = len_n;
-      xv_c = xv_n;
-      gi_n = gi_nn;
-      xv_n = xv_nn;
+      const bool alive = cur < end;
+      if (!__any_sync(FULL, alive)) break;  // queue and pipeline are empty too (loop above ran dry)
+      // chunks are fetched two boundaries ahead of their use (a staged record carries the first two)
+      if (alive && cur + 8 < end) nnbuf = *reinterpret_cast<const uint2*>(p.idx + cur + 8);
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const unsigned off = ((s4 < 2 ? buf.x : buf.y) >> (16 * (s4 & 1))) & 0xFFFFu;
+        bool pend = alive && off != 0xFFFFu;
+        unsigned char* __restrict__ tg = tag + (off >> 3);
+        double* __restrict__ a = reinterpret_cast<double*>(accb + off);
+        if (pend) *tg = (unsigned char)lane;
+        __syncwarp();
+        {
+          const bool win = pend && (*tg == (unsigned char)lane);
+          if (win) *a += x;
+          pend = pend && !win;
+        }
+        while (__any_sync(FULL, pend)) {  // rare: two genes of this step share a set
+          if (pend) *tg = (unsigned char)lane;
+          __syncwarp();
+          const bool win = pend && (*tg == (unsigned char)lane);
+          if (win) *a += x;
+          pend = pend && !win;
+        }
+      }
+      cur += 4;
     }
 
     // ---- flush tile t of column j: fused epilogue, coalesced streaming store, re-zero ----
+    // (4 rows per lane at a time with the global loads issued first: the partial sums of the gather
+    //  pass and the per-set scales would otherwise each expose a DRAM / L2 round trip)
     const int sbase = t * p.Ts;
     const int tl = min(p.Ts, p.S - sbase);
     double* __restrict__ o = p.out + j * p.ld + sbase;
-    for (int l = lane; l < tl; l += 32) {
-      double v = acc[l];
-      acc[l] = 0.0;
-      if (p.accumulate) v += __ldcs(o + l);  // partial sums of the gather pass
-      if (p.final) v = score_epilogue(v, sbase + l, j, fb, GENERAL ? p.mode : XF_IDENT, p.inv, p.ns, p.colscale);
-      __stcs(o + l, v);
+    const double* __restrict__ invt = p.inv + sbase;
+    const double* __restrict__ nst = p.ns + sbase;
+    const bool rankmode = GENERAL && p.mode >= XF_SING;
+    const double csj = (p.final && p.colscale) ? p.colscale[j] : 1.0;
+    for (int l0 = lane; l0 < tl; l0 += 128) {
+      double part[4], iv[4], nv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + 32 * u;
+        part[u] = 0.0; iv[u] = 1.0; nv[u] = 0.0;
+        if (l < tl) {
+          if (p.accumulate) part[u] = __ldcs(o + l);
+          if (p.final) {
+            iv[u] = invt[l];
+            if (rankmode) nv[u] = nst[l];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + 32 * u;
+        if (l < tl) {
+          double v = acc[l] + part[u];
+          acc[l] = 0.0;
+          if (p.final) {
+            if (rankmode) v += fb * nv[u];
+            v = v * iv[u] * csj;
+          }
+          __stcs(o + l, v);
+        }
+      }
     }
     __syncwarp();
   }
@@ -185,10 +228,12 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
   int warps = 8;
   if (const char* w = getenv("PLAIDGPU_WARPS")) {  // tuning knob (bench / profiling only)
     const int v = atoi(w);
-    if (v == 1 || v == 2 || v == 4 || v == 8) warps = v;
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) warps = v;
   }
   const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin - 1024;  // leave the 1 KB reserve
-  int32_t ts_max = (int32_t)((smem_max - (size_t)warps * 32 * 16) / (8 * warps));
+  // per warp: Ts fp64 accumulators + Ts byte tags (16-byte aligned) + 32 staged gene records of 32 B
+  int32_t ts_max = (int32_t)((smem_max / warps - 1024 - 16) / 9);
+  if (ts_max > 8160) ts_max = 8160;  // tile-local byte offsets are 16-bit (0xFFFF = padding)
   ts_max = (ts_max / 32) * 32;
   if (ts_max > 65536) ts_max = 65536;
   int32_t Ts, T;
@@ -203,16 +248,15 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
     if (Ts < 32) Ts = 32;
   }
   cfg->warps = warps;
-  cfg->smem = (size_t)warps * Ts * sizeof(double) + (size_t)warps * 32 * 16;  // + per-warp staging
+  cfg->smem = (size_t)warps * ((size_t)Ts * sizeof(double) + (size_t)((Ts + 15) & ~15) + 1024);
   // persistent grid: SM count x resident CTAs per SM
   int per_sm = 0;
-  const void* fns[4] = {(const void*)k_score<false, false>, (const void*)k_score<false, true>,
-                        (const void*)k_score<true, false>, (const void*)k_score<true, true>};
-  for (int i = 0; i < 4; ++i) {
+  const void* fns[2] = {(const void*)k_scatter<false>, (const void*)k_scatter<true>};
+  for (int i = 0; i < 2; ++i) {
     e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return e;
   }
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score<false, true>, warps * 32, cfg->smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter<true>, warps * 32, cfg->smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
@@ -224,17 +268,12 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
 
 cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st) {
   if (p.N <= 0) return cudaSuccess;
-  const bool general = (p.mode != XF_IDENT);
+  if (dense) return cudaErrorInvalidValue;  // dense X goes through the gather passes only
   int64_t grid = cfg.ctas;
   if (grid > p.N) grid = p.N;
   dim3 g((unsigned)grid), b((unsigned)cfg.warps * 32);
-  if (dense) {
-    if (general) k_score<true, true><<<g, b, cfg.smem, st>>>(p);
-    else k_score<true, false><<<g, b, cfg.smem, st>>>(p);
-  } else {
-    if (general) k_score<false, true><<<g, b, cfg.smem, st>>>(p);
-    else k_score<false, false><<<g, b, cfg.smem, st>>>(p);
-  }
+  if (p.mode != XF_IDENT) k_scatter<true><<<g, b, cfg.smem, st>>>(p);
+  else k_scatter<false><<<g, b, cfg.smem, st>>>(p);
   return cudaGetLastError();
 }
 

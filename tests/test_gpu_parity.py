@@ -230,8 +230,8 @@ def test_properties_linearity_and_column_independence(gpu_ctx):
     Gn = pb.NamedMatrix(G, names)
     a = pb.plaid(pb.NamedMatrix(X, names), Gn, stats="sum", normalize=False, ctx=gpu_ctx).mat
     assert a.shape == (S, N)
-    # repeated set blocks give identical rows
-    assert np.array_equal(a[:2000], a[2000:4000])
+    # repeated set blocks give the same rows (the order of the fp64 adds may differ between tiles)
+    assert np.allclose(a[:2000], a[2000:4000], rtol=1e-13, atol=0)
     # column independence: scoring a column subset gives the same bits (sharding invariant)
     sub = pb.plaid(pb.NamedMatrix(X[:, 100:228], names), Gn, stats="sum", normalize=False, ctx=gpu_ctx).mat
     assert np.array_equal(sub, a[:, 100:228])
