@@ -156,23 +156,26 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
       if (alive && cur + 8 < end) nnbuf = *reinterpret_cast<const uint2*>(p.idx + cur + 8);
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
-        const unsigned off = ((s4 < 2 ? buf.x : buf.y) >> (16 * (s4 & 1))) & 0xFFFFu;
-        bool pend = alive && off != 0xFFFFu;
+        // branch-free fast path: inactive lanes are pointed at set 0 and simply never win
+        const unsigned raw = ((s4 < 2 ? buf.x : buf.y) >> (16 * (s4 & 1))) & 0xFFFFu;
+        bool pend = alive && raw != 0xFFFFu;
+        const unsigned off = pend ? raw : 0u;
         unsigned char* __restrict__ tg = tag + (off >> 3);
-        double* __restrict__ a = reinterpret_cast<double*>(accb + off);
+        volatile double* a = reinterpret_cast<volatile double*>(accb + off);
         if (pend) *tg = (unsigned char)lane;
-        __syncwarp();
-        {
-          const bool win = pend && (*tg == (unsigned char)lane);
-          if (win) *a += x;
-          pend = pend && !win;
-        }
+        // (same warp, program order: every lane's tag store is performed before any lane's tag load)
+        const unsigned tv = *reinterpret_cast<volatile unsigned char*>(tg);
+        const double v0 = *a;
+        const bool win = pend && tv == (unsigned)lane;
+        if (win) *a = v0 + x;
+        pend = pend && !win;
         while (__any_sync(FULL, pend)) {  // rare: two genes of this step share a set
           if (pend) *tg = (unsigned char)lane;
           __syncwarp();
-          const bool win = pend && (*tg == (unsigned char)lane);
-          if (win) *a += x;
-          pend = pend && !win;
+          const bool w2 = pend && (*reinterpret_cast<volatile unsigned char*>(tg) == (unsigned char)lane);
+          if (w2) *a = *a + x;
+          pend = pend && !w2;
+          __syncwarp();
         }
       }
       cur += 4;
