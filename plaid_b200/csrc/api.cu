@@ -234,27 +234,35 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         const int32_t r = g2x[c->Gi[q]];
         if (r >= 0 && !in_block(r)) setof[fill[r]++] = s;
       }
-    // per (row, tile) lists of 16-bit byte offsets (tile-local set id * 8), each padded to a multiple
-    // of 4 entries with 0xFFFF so that a lane always reads whole 8-byte chunks
+    // one 16-byte record per (row, tile): {u32 overflow offset, u16 length, u16 0, u16 entry[4]}; entries
+    // are byte offsets (tile-local set id * 8); lists longer than 4 continue in the overflow array in
+    // chunks of 4 padded with 0xFFFF
     idx.clear();
-    idx.reserve((size_t)nnz_scatter + (size_t)nnz_scatter / 4 + 16);
-    ptr.assign((size_t)P * (T + 1), 0);
+    idx.reserve((size_t)nnz_scatter + 16);
+    ptr.assign((size_t)P * T * 4, 0);
     for (int32_t r = 0; r < P; ++r) {
       uint32_t e0 = rowcnt[r];
       const uint32_t e1 = rowcnt[r + 1];
-      uint32_t* pr = ptr.data() + (size_t)r * (T + 1);
       for (int32_t t = 0; t < T; ++t) {
-        pr[t] = (uint32_t)idx.size();
+        uint32_t* rc = ptr.data() + ((size_t)r * T + t) * 4;
         const int32_t hi = (t + 1) * Ts;
+        uint16_t in4[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+        uint32_t n = 0;
+        rc[0] = (uint32_t)idx.size();
         while (e0 < e1 && setof[e0] < hi) {
-          idx.push_back((uint16_t)((setof[e0] - t * Ts) * 8));
+          const uint16_t off = (uint16_t)((setof[e0] - t * Ts) * 8);
+          if (n < 4) in4[n] = off; else idx.push_back(off);
+          ++n;
           ++e0;
         }
         while (idx.size() & 3) idx.push_back((uint16_t)0xFFFFu);
+        if (n > 0xFFFFu) return fail(c, PLAIDGPU_ERR_ARG, "gene-set list too long for one tile");
+        rc[1] = n;
+        rc[2] = (uint32_t)in4[0] | ((uint32_t)in4[1] << 16);
+        rc[3] = (uint32_t)in4[2] | ((uint32_t)in4[3] << 16);
       }
-      pr[T] = (uint32_t)idx.size();
     }
-    for (int k = 0; k < 8; ++k) idx.push_back((uint16_t)0xFFFFu);  // chunk prefetch may read one chunk past a list
+    for (int k = 0; k < 8; ++k) idx.push_back((uint16_t)0xFFFFu);
   }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
   for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76

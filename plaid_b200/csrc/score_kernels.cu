@@ -36,10 +36,10 @@ namespace plaidgpu {
 // path.  Lists are padded to multiples of 4 entries (0xFFFF): all lanes cross chunk boundaries
 // together and refills happen only there.
 struct __align__(16) GeneRec {
-  uint32_t cur, end;
+  uint32_t rest;   // offset of chunk 1 in the overflow array
+  uint32_t nchunk; // number of 4-entry chunks of the list (chunk 0 is inline in the tile record)
   double x;
-  uint2 chunk;   // entries [cur, cur + 4)
-  uint2 chunk1;  // entries [cur + 4, cur + 8) (garbage when the list is shorter; never used then)
+  uint2 chunk0, chunk1;
 };
 
 template <bool GENERAL>
@@ -59,7 +59,6 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
   const unsigned lt = (1u << lane) - 1u;
 
   const int T = p.T;
-  const int stride = T + 1;
   const int64_t ncols_cta = (p.N - blockIdx.x + gridDim.x - 1) / gridDim.x;  // columns of this CTA
   const int64_t nitems = ncols_cta * T;
 
@@ -70,42 +69,41 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
     const int64_t c0 = p.xp[j], c1 = p.xp[j + 1];
     double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
     if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
-    const uint32_t* __restrict__ ptr_t = p.ptr + t;
-
     // ---- batch pipeline (lane i prepares entry i of a batch) ---------------------------------
+    // adjacency format: one 16-byte record per (X row, tile) = {overflow offset, list length, 4 inline
+    // entries}; longer lists continue in the overflow array in chunks of 4 (padded with 0xFFFF).  One
+    // scattered 16-byte load therefore yields the pointer AND the first chunk of a (gene, tile) list.
+    const uint4* __restrict__ trec = reinterpret_cast<const uint4*>(p.ptr) + t;
     int64_t ebase = c0;          // first entry of the batch whose (row, value) load is issued next
     int gi1 = -1;                // R1: row index + value loaded
     double x1 = 0.0;
-    uint32_t cur2 = 0, end2 = 0; // R2: row pointers loaded
+    uint32_t rest2 = 0, nch2 = 0;  // R2: tile record loaded
+    uint2 c02 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     double x2 = 0.0;
-    uint32_t cur3 = 0, end3 = 0; // R3: first chunk loaded -> ready to be staged
+    uint32_t rest3 = 0, nch3 = 0;  // R3: second chunk loaded -> ready to be staged
+    uint2 c03 = c02, c13 = c02;
     double x3 = 0.0;
-    uint2 ch3 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), ch3b = ch3;
     int qhead = 0, qcount = 0;   // staged batch: records [qhead, qcount) are unassigned (warp-uniform)
 
-    // one rotation: stage R3 into shared memory, R2 -> R3 (+chunk load), R1 -> R2 (+pointer loads),
-    // issue the (row, value) loads of the next batch
     auto rotate = [&]() {
-      const bool have = cur3 < end3;
+      const bool have = nch3 > 0;
       const unsigned m = __ballot_sync(FULL, have);
       if (have) {
         GeneRec r;
-        r.cur = cur3; r.end = end3; r.x = x3; r.chunk = ch3; r.chunk1 = ch3b;
+        r.rest = rest3; r.nchunk = nch3; r.x = x3; r.chunk0 = c03; r.chunk1 = c13;
         rec[__popc(m & lt)] = r;
       }
       qhead = 0;
       qcount = __popc(m);
       __syncwarp();
-      cur3 = cur2; end3 = end2; x3 = x2;
-      if (cur3 < end3) {
-        ch3 = *reinterpret_cast<const uint2*>(p.idx + cur3);
-        ch3b = *reinterpret_cast<const uint2*>(p.idx + cur3 + 4);
-      }
-      cur2 = 0; end2 = 0;
+      rest3 = rest2; nch3 = nch2; x3 = x2; c03 = c02;
+      if (nch3 > 1) c13 = *reinterpret_cast<const uint2*>(p.idx + rest3);
+      nch2 = 0;
       if (gi1 >= 0) {
-        const uint32_t* pp = ptr_t + (size_t)gi1 * stride;
-        cur2 = pp[0];
-        end2 = pp[1];
+        const uint4 tr = __ldg(trec + (size_t)gi1 * T);
+        rest2 = tr.x;
+        nch2 = ((tr.y & 0xFFFFu) + 3u) >> 2;
+        c02 = make_uint2(tr.z, tr.w);
         x2 = x1;
         if (GENERAL) x2 = xform_value(p.mode, x1, p.a0, p.a1) - (p.mode >= XF_SING ? fb : 0.0);
       }
@@ -121,13 +119,14 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
     rotate();
     rotate();
     int remaining = (int)((c1 - c0 + 31) >> 5);  // batches still to be staged (one per further rotation)
-    uint32_t cur = 0, end = 0;   // this lane's active list
+    uint32_t ck = 0, nck = 0, rest = 0;  // this lane's active list: chunk ck of nck
     double x = 0.0;
     uint2 buf = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), nbuf = buf, nnbuf = buf;
 
     for (;;) {
       // ---- chunk boundary (every 4 steps, all lanes together): advance chunk / take a new gene ----
-      bool need = cur >= end;
+      ++ck;
+      bool need = ck >= nck;
       if (!need) {
         buf = nbuf;
         nbuf = nnbuf;
@@ -144,16 +143,16 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
         const int pos = qhead + __popc(nm & lt);
         if (need && pos < qcount) {
           const GeneRec r = rec[pos];
-          cur = r.cur; end = r.end; x = r.x; buf = r.chunk; nbuf = r.chunk1;
+          rest = r.rest; nck = r.nchunk; ck = 0; x = r.x; buf = r.chunk0; nbuf = r.chunk1;
           need = false;
         }
         qhead += __popc(nm);
         __syncwarp();
       }
-      const bool alive = cur < end;
+      const bool alive = ck < nck;
       if (!__any_sync(FULL, alive)) break;  // queue and pipeline are empty too (loop above ran dry)
       // chunks are fetched two boundaries ahead of their use (a staged record carries the first two)
-      if (alive && cur + 8 < end) nnbuf = *reinterpret_cast<const uint2*>(p.idx + cur + 8);
+      if (alive && ck + 2 < nck) nnbuf = *reinterpret_cast<const uint2*>(p.idx + rest + 4 * (ck + 1));
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
         // branch-free fast path: inactive lanes are pointed at set 0 and simply never win
@@ -178,7 +177,6 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
           __syncwarp();
         }
       }
-      cur += 4;
     }
 
     // ---- flush tile t of column j: fused epilogue, coalesced streaming store, re-zero ----
@@ -228,7 +226,7 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return e;
-  int warps = 8;
+  int warps = 16;
   if (const char* w = getenv("PLAIDGPU_WARPS")) {  // tuning knob (bench / profiling only)
     const int v = atoi(w);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) warps = v;
