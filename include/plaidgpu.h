@@ -57,7 +57,7 @@ extern "C" {
 #define PLAIDGPU_SSGSEA 3  /* replaid.ssgsea()   R/plaid.R:244-255 */
 #define PLAIDGPU_UCELL 4   /* replaid.ucell()    R/plaid.R:276-282 */
 #define PLAIDGPU_AUCELL 5  /* replaid.aucell()   R/plaid.R:304-309 */
-#define PLAIDGPU_GSVA 6    /* replaid.gsva(rowtf="z")  R/plaid.R:338-363 */
+#define PLAIDGPU_GSVA 6    /* replaid.gsva(rowtf="z")  R/plaid.R:338-363 (rowtf="ecdf" is not on the GPU path) */
 
 /* ties.method of base::rank / colRanks (R/plaid.R:589-650) */
 #define PLAIDGPU_TIES_AVERAGE 0
@@ -95,6 +95,8 @@ typedef struct plaidgpu_opts {
   int64_t nrow_x;        /* nrow(X) used by replaid.sing (rX / nrow(X)); 0 -> X.P  R/plaid.R:216 */
   const double* matg_full_colsums; /* ucell: colSums(matG != 0) over ALL rows of matG [S] (host);
                                       NULL -> taken from plaidgpu_set_genesets      R/plaid.R:280 */
+  const double* row_mean;  /* gsva: rowMeans(X) over ALL samples of ALL shards [P] (host); NULL -> this shard only */
+  const double* row_sd;    /* gsva: rowSds(X) (sample SD, n-1) [P] (host); NULL -> this shard only  R/plaid.R:343 */
 } plaidgpu_opts;
 
 /* cross-shard scalars.  Produced per shard by *_begin (local values), combined by the
@@ -171,6 +173,14 @@ int plaidgpu_score_finish(plaidgpu_ctx* ctx, const plaidgpu_scalars* scal, doubl
  * y is X restricted/ordered by rowmap as in plaidgpu_score.  out: S x N dense. */
 int plaidgpu_crossprod(plaidgpu_ctx* ctx, const plaidgpu_matrix* Y, const int32_t* rowmap,
                        const double* colscale, int out_location, double* out);
+
+/* Per-row sums across the columns of this shard, for replaid.gsva's row z-transform
+ * (rowMeans / rowSds, R/plaid.R:343,365-370) when X is column-sharded:
+ *   mean == NULL : out[r] = sum_j X[r, j]
+ *   mean != NULL : out[r] = sum_j (X[r, j] - mean[r])^2     (mean: host double[P])
+ * The caller adds the shards' vectors, divides by N_total (resp. N_total - 1, sqrt) and passes the
+ * results as opts.row_mean / opts.row_sd.  out: host double[P]. */
+int plaidgpu_row_moments(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, const double* mean, double* out);
 
 /* ---- ranking ---------------------------------------------------------------------- */
 

@@ -343,17 +343,23 @@ def mat_rowsds(Xm) -> np.ndarray:
     """`mat.rowsds` (R/plaid.R:365-370): sample SD (n-1) per row, two-pass."""
     D = Xm.toarray() if _is_sparse(Xm) else np.asarray(Xm, dtype=np.float64)
     n = D.shape[1]
-    mu = D.mean(axis=1, keepdims=True)
+    mu = row_means(D)[:, None]
     if n < 2:
         return np.full(D.shape[0], np.nan)
-    return np.sqrt(((D - mu) ** 2).sum(axis=1) / (n - 1))
+    ss = ((D - mu) ** 2).astype(np.longdouble).sum(axis=1).astype(np.float64)
+    return np.sqrt(ss / (n - 1))
+
+
+def row_means(D: np.ndarray) -> np.ndarray:
+    """rowMeans(X): R accumulates each row in long double, then divides by ncol."""
+    return (D.astype(np.longdouble).sum(axis=1).astype(np.float64)) / D.shape[1]
 
 
 def replaid_gsva(X: Named, matG: Named, tau: float = 0.0, rowtf: str = "z"):
     """`replaid.gsva` (R/plaid.R:338-363), rowtf in {"z", "ecdf"}."""
     D = X.mat.toarray() if _is_sparse(X.mat) else np.asarray(X.mat, dtype=np.float64)
     if rowtf == "z":  # :341-343
-        zX = (D - D.mean(axis=1, keepdims=True)) / (1e-8 + mat_rowsds(D))[:, None]
+        zX = (D - row_means(D)[:, None]) / (1e-8 + mat_rowsds(D))[:, None]
     elif rowtf == "ecdf":  # :344-346  ecdf(x)(x) = fraction of row values <= x
         zX = np.empty_like(D)
         for g in range(D.shape[0]):

@@ -30,7 +30,8 @@ class Opts(C.Structure):
                 ("ignore_zero", C.c_int32), ("remove_log2", C.c_int32), ("score_mean", C.c_int32),
                 ("out_location", C.c_int32), ("tile_sets", C.c_int32), ("alpha", C.c_double),
                 ("rmax", C.c_double), ("auc_max_rank", C.c_double), ("tau", C.c_double),
-                ("nrow_x", C.c_int64), ("matg_full_colsums", C.c_void_p)]
+                ("nrow_x", C.c_int64), ("matg_full_colsums", C.c_void_p), ("row_mean", C.c_void_p),
+                ("row_sd", C.c_void_p)]
 
 
 class Scalars(C.Structure):
@@ -54,6 +55,7 @@ SYMBOLS = {
     "plaidgpu_combine_medians": (C.c_int, [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Scalars)]),
     "plaidgpu_score_finish": (C.c_int, [C.c_void_p, C.POINTER(Scalars), C.c_void_p]),
     "plaidgpu_crossprod": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "plaidgpu_row_moments": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.c_void_p]),
     "plaidgpu_colranks": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "plaidgpu_normalize_medians": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "plaidgpu_launch_count": (C.c_int64, [C.c_void_p]),

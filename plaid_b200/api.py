@@ -388,3 +388,15 @@ def replaid_aucell(X: NamedMatrix, matG: NamedMatrix, aucMaxRank: Optional[float
     """`replaid.aucell(X, matG, aucMaxRank=ceiling(0.05*nrow(X)))` (R/plaid.R:304-309)."""
     a = float(aucMaxRank) if aucMaxRank is not None else float(math.ceil(0.05 * X.shape[0]))
     return _score(X, matG, dict(scorer=L.AUCELL, auc_max_rank=a), ctx, out)
+
+
+def replaid_gsva(X: NamedMatrix, matG: NamedMatrix, tau: float = 0.0, rowtf: str = "z", *, ctx=None, out=None):
+    """`replaid.gsva(X, matG, tau=0, rowtf="z")` (R/plaid.R:338-363).  `rowtf="ecdf"` ranks every gene
+    ACROSS samples and is not on the GPU path; any other value is the reference's error."""
+    if isinstance(rowtf, (list, tuple)):
+        rowtf = rowtf[0]
+    if rowtf == "ecdf":
+        raise NotImplementedError("replaid.gsva(rowtf='ecdf') is not available on the GPU path")
+    if rowtf != "z":
+        raise ValueError("Error: unknown row transform" + str(rowtf))  # R/plaid.R:348
+    return _score(X, matG, dict(scorer=L.GSVA, tau=float(tau)), ctx, out)

@@ -80,7 +80,7 @@ struct plaidgpu_ctx {
   const int32_t* xp = nullptr;
   const int32_t* xi = nullptr;
   const double* xx = nullptr;
-  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32;
+  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb;
   double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
   bool need_norm = false;
   std::vector<double> h_med_all, h_med_nz, h_colmin;
@@ -353,6 +353,37 @@ int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X) {
   return PLAIDGPU_OK;
 }
 
+// gsva works on a dense matrix: expand a CSC shard on the device (zeros filled)
+int make_dense(plaidgpu_ctx* c) {
+  if (c->dense) return PLAIDGPU_OK;
+  const int64_t total = (int64_t)c->P * c->N;
+  CK(c->b_dense.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+  CK(launch_densify(c->xp, c->xi, c->xx, c->P, c->N, c->b_dense.as<double>(), c->stream));
+  c->launches += 1;
+  c->dense = true;
+  c->xp = nullptr;
+  c->xi = nullptr;
+  c->xx = c->b_dense.as<double>();
+  c->nnz = total;
+  return PLAIDGPU_OK;
+}
+
+// out_host[r] = sum_j x[r,j] or sum_j (x[r,j] - mean[r])^2 of the (dense) loaded matrix
+int row_moments(plaidgpu_ctx* c, const double* mean_host, double* out_host) {
+  CK(c->b_rowa.reserve((size_t)c->P * sizeof(double)));
+  CK(c->b_rowb.reserve((size_t)c->P * sizeof(double)));
+  const double* dmean = nullptr;
+  if (mean_host) {
+    CK(cudaMemcpyAsync(c->b_rowb.p, mean_host, (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dmean = c->b_rowb.as<double>();
+  }
+  CK(launch_row_moments(c->xx, c->P, c->N, dmean, c->b_rowa.as<double>(), c->stream));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out_host, c->b_rowa.p, (size_t)c->P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PLAIDGPU_OK;
+}
+
 bool is_rank_scorer(int s) {
   return s == PLAIDGPU_SING || s == PLAIDGPU_SSGSEA || s == PLAIDGPU_UCELL || s == PLAIDGPU_AUCELL;
 }
@@ -438,7 +469,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
                     &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
-                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32};
+                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -505,9 +536,9 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   c->computed = false;
   c->opts = *opts;
   if (opts->scorer < PLAIDGPU_PLAID || opts->scorer > PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
-  if (opts->scorer == PLAIDGPU_GSVA) return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva is not available in this build");
   if (opts->scorer == PLAIDGPU_SSGSEA && !(1.0 + opts->alpha > 0.0)) return fail(c, PLAIDGPU_ERR_ARG, "ssgsea needs alpha > -1");
-  int rc = build_plan(c, X->P, rowmap, opts->tile_sets, X->kind == PLAIDGPU_DENSE);
+  // gsva scores a dense z-matrix whatever the storage of X
+  int rc = build_plan(c, X->P, rowmap, opts->tile_sets, X->kind == PLAIDGPU_DENSE || opts->scorer == PLAIDGPU_GSVA);
   if (rc) return rc;
   rc = load_matrix(c, X);
   if (rc) return rc;
@@ -530,6 +561,46 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     }
     local->x_min = mn;
     local->x_max = mx;
+  }
+
+  if (opts->scorer == PLAIDGPU_GSVA) {
+    // zX <- (X - rowMeans(X)) / (1e-8 + rowSds(X)); rX <- sign(zX) * colRanks(|zX|)   (R/plaid.R:343,351)
+    rc = make_dense(c);
+    if (rc) return rc;
+    std::vector<double> mean((size_t)c->P), sd((size_t)c->P);
+    if (opts->row_mean && opts->row_sd) {
+      memcpy(mean.data(), opts->row_mean, (size_t)c->P * sizeof(double));
+      memcpy(sd.data(), opts->row_sd, (size_t)c->P * sizeof(double));
+    } else {  // single shard: both passes locally
+      rc = row_moments(c, nullptr, mean.data());
+      if (rc) return rc;
+      for (int32_t r = 0; r < c->P; ++r) mean[r] /= (double)c->N;
+      rc = row_moments(c, mean.data(), sd.data());
+      if (rc) return rc;
+      for (int32_t r = 0; r < c->P; ++r) sd[r] = c->N > 1 ? sqrt(sd[r] / (double)(c->N - 1)) : NAN;
+    }
+    CK(c->b_rowa.reserve((size_t)c->P * sizeof(double)));
+    CK(c->b_rowb.reserve((size_t)c->P * sizeof(double)));
+    CK(cudaMemcpyAsync(c->b_rowa.p, mean.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->b_rowb.p, sd.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+    CK(c->b_colmax.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(launch_ztransform(c->xx, c->P, c->N, c->b_rowa.as<double>(), c->b_rowb.as<double>(), c->b_rank.as<double>(), c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // mean / sd host vectors die with this scope
+    // signed average ranks of the dense z columns, in place (each position is read, then written, by one thread)
+    CK(launch_rank_dense(c->b_rank.as<double>(), c->P, c->N, PLAIDGPU_TIES_AVERAGE, 1, c->b_rank.as<double>(),
+                         c->b_colmax.as<double>(), c->stream));
+    c->launches += 2;
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    double mn, mx;
+    rc = device_minmax(c, c->b_colmax.as<double>(), c->N, &mn, &mx);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+    c->ms[3] = ms;
+    local->rank_max = mx;  // max(abs(rX))   (R/plaid.R:352)
+    c->score_vals = c->b_rank.as<double>();
   }
 
   if (is_rank_scorer(opts->scorer)) {
@@ -630,11 +701,17 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       p.a1 = o.auc_max_rank > 0.0 ? o.auc_max_rank : ceil(0.05 * (double)c->P);
       c->need_norm = true;
       break;
+    case PLAIDGPU_GSVA:
+      p.mode = XF_GSVA;
+      p.a0 = scal->rank_max;
+      p.a1 = o.tau;
+      c->need_norm = true;
+      break;
     default:
       return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
   }
   p.inv = mean ? c->d_inv_mean.as<double>() : c->d_inv_one.as<double>();
-  if (is_rank_scorer(o.scorer)) {
+  if (is_rank_scorer(o.scorer) || o.scorer == PLAIDGPU_GSVA) {
     if (c->dense) {
       // dense input: transform the dense rank matrix in place, then plain product
       CK(launch_xform_dense(c->b_rank.as<double>(), c->b_rank.as<double>(), c->nnz, p.mode, p.a0, p.a1, c->stream));
@@ -858,6 +935,19 @@ int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t*
   }
   if (rc) return rc;
   return plaidgpu_score_finish(c, &s, out);
+}
+
+int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double* mean, double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  c->in_call = false;
+  c->computed = false;
+  int rc = load_matrix(c, X);
+  if (rc) return rc;
+  rc = make_dense(c);
+  if (rc) return rc;
+  return row_moments(c, mean, out);
 }
 
 // -----------------------------------------------------------------------------------------

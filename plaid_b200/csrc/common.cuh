@@ -21,7 +21,8 @@ enum XformMode : int {
   XF_SING = 3,      // r / a0 - 0.5, a0 = nrow(X)                         (R/plaid.R:216)
   XF_SSGSEA = 4,    // r^(1+a1) / a0 - 0.5, a0 = max(r^(1+a1))            (R/plaid.R:246-251)
   XF_UCELL = 5,     // min(a0 - r, a1), a0 = max(r), a1 = rmax + 1         (R/plaid.R:278)
-  XF_AUCELL = 6     // 1.08 * max((r - (a0 - a1)) / a1, 0), a1 = aucMaxRank (R/plaid.R:306)
+  XF_AUCELL = 6,    // 1.08 * max((r - (a0 - a1)) / a1, 0), a1 = aucMaxRank (R/plaid.R:306)
+  XF_GSVA = 7       // r / a0, then sign * |.|^(1 + a1) when a1 > 0 (dense only)  (R/plaid.R:352-357)
 };
 
 struct ScoreParams {
@@ -135,6 +136,15 @@ cudaError_t launch_expand_ranks(const int32_t* xp, const int32_t* xi, const doub
 // elementwise transform of a dense matrix with an XformMode (rank scorers on dense input)
 cudaError_t launch_xform_dense(const double* in, double* out, int64_t n, int mode, double a0,
                                double a1, cudaStream_t st);
+// gsva row z-transform (dense P x N, column-major):
+//   launch_row_moments: out[r] = sum_j x[r,j]  (mean == nullptr)  or  sum_j (x[r,j] - mean[r])^2, compensated sums
+//   launch_ztransform : z[r,j] = (x[r,j] - mean[r]) / (1e-8 + sd[r])
+//   launch_densify    : CSC -> dense (zeros filled)
+cudaError_t launch_row_moments(const double* x, int32_t P, int64_t N, const double* mean, double* out, cudaStream_t st);
+cudaError_t launch_ztransform(const double* x, int32_t P, int64_t N, const double* mean, const double* sd, double* z,
+                              cudaStream_t st);
+cudaError_t launch_densify(const int32_t* xp, const int32_t* xi, const double* xx, int32_t P, int64_t N, double* dense,
+                           cudaStream_t st);
 // max nnz of any column of a device CSC pointer array
 cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st);
 
@@ -147,6 +157,10 @@ __device__ __forceinline__ double xform_value(int mode, double v, double a0, dou
     case XF_SSGSEA: return (a1 != 0.0 ? pow(v, 1.0 + a1) : v) / a0 - 0.5;
     case XF_UCELL: return fmin(a0 - v, a1);
     case XF_AUCELL: return 1.08 * fmax((v - (a0 - a1)) / a1, 0.0);
+    case XF_GSVA: {
+      const double r = v / a0;
+      return a1 > 0.0 ? copysign(pow(fabs(r), 1.0 + a1), r) * (r == 0.0 ? 0.0 : 1.0) : r;
+    }
     default: return v;
   }
 }

@@ -223,6 +223,35 @@ __global__ void __launch_bounds__(256) k_max_col_nnz(const int32_t* __restrict__
   if ((threadIdx.x & 31) == 0) atomicMax(res, m);
 }
 
+// one thread per row, columns in order: deterministic; Neumaier-compensated so the fp64 result is the
+// correctly rounded sum in all but pathological cases (R sums rows in long double)
+__global__ void __launch_bounds__(128) k_row_moments(const double* __restrict__ x, int32_t P, int64_t N,
+                                                     const double* __restrict__ mean, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P) return;
+  const double mu = mean ? mean[r] : 0.0;
+  double s = 0.0, comp = 0.0;
+  for (int64_t j = 0; j < N; ++j) {
+    double v = x[j * (int64_t)P + r];
+    if (mean) {
+      v -= mu;
+      v *= v;
+    }
+    const double t = s + v;
+    comp += (fabs(s) >= fabs(v)) ? (s - t) + v : (v - t) + s;
+    s = t;
+  }
+  out[r] = s + comp;
+}
+
+__global__ void __launch_bounds__(256) k_ztransform(const double* __restrict__ x, int32_t P, int64_t N,
+                                                    const double* __restrict__ mean, const double* __restrict__ sd,
+                                                    double* __restrict__ z) {
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x)
+    for (int r = threadIdx.x; r < P; r += blockDim.x)
+      z[j * (int64_t)P + r] = (x[j * (int64_t)P + r] - mean[r]) / (1e-8 + sd[r]);
+}
+
 int sm_count() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -315,6 +344,26 @@ cudaError_t launch_xform_dense(const double* in, double* out, int64_t n, int mod
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
   k_xform_dense<<<(unsigned)grid, 256, 0, st>>>(in, out, n, mode, a0, a1);
   return cudaGetLastError();
+}
+
+cudaError_t launch_row_moments(const double* x, int32_t P, int64_t N, const double* mean, double* out, cudaStream_t st) {
+  if (P <= 0) return cudaSuccess;
+  k_row_moments<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(x, P, N, mean, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ztransform(const double* x, int32_t P, int64_t N, const double* mean, const double* sd, double* z,
+                              cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t grid = (int64_t)sm_count() * 8;
+  if (grid > N) grid = N;
+  k_ztransform<<<(unsigned)grid, 256, 0, st>>>(x, P, N, mean, sd, z);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_densify(const int32_t* xp, const int32_t* xi, const double* xx, int32_t P, int64_t N, double* dense,
+                           cudaStream_t st) {
+  return launch_expand_ranks(xp, xi, xx, nullptr, P, N, dense, st);  // same scatter: zeros filled, stored entries placed
 }
 
 cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st) {

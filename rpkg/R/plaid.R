@@ -113,3 +113,10 @@ replaid.ucell <- function(X, matG, rmax = 1500) {                           # R/
 replaid.aucell <- function(X, matG, aucMaxRank = ceiling(0.05 * nrow(X))) { # R/plaid.R:304-309
   .score(X, matG, list(scorer = 5L, auc_max_rank = as.numeric(aucMaxRank)))
 }
+
+replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1]) {      # R/plaid.R:338-363
+  rowtf <- rowtf[1]
+  if (rowtf == "ecdf") stop("replaid.gsva(rowtf = 'ecdf') is not available on the GPU path")
+  if (rowtf != "z") stop("Error: unknown row transform", rowtf)              # R/plaid.R:348
+  .score(X, matG, list(scorer = 6L, tau = as.numeric(tau)))
+}

@@ -77,6 +77,7 @@ SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim,
   o.alpha = opt_dbl(opts, "alpha", o.alpha);
   o.rmax = opt_dbl(opts, "rmax", o.rmax);
   o.auc_max_rank = opt_dbl(opts, "auc_max_rank", o.auc_max_rank);
+  o.tau = opt_dbl(opts, "tau", o.tau);
   o.nrow_x = (int64_t)opt_dbl(opts, "nrow_x", 0.0);
   SEXP cs = list_get(opts, "matg_full_colsums");
   o.matg_full_colsums = cs == R_NilValue ? NULL : REAL(cs);

@@ -129,6 +129,23 @@ def test_rank_scorers_dense_input(gpu_ctx):
     assert rel_err(pb.replaid_scse(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_scse(Xo, Go).mat) < 1e-9
 
 
+def test_gsva_z(fixture_mats, golden, gpu_ctx):
+    """replaid.gsva(rowtf="z"): row z-transform across samples, signed dense ranks, plaid (R/plaid.R:338-363)."""
+    Xg, Gg, _, _ = _named(*fixture_mats)
+    assert rel_err(pb.replaid_gsva(Xg, Gg, ctx=gpu_ctx).mat, golden["gsva_z"]) < 1e-9  # sparse input, densified
+    P, N, S = 1200, 40, 150
+    X = synth.dense_x_numpy(P, N, seed=35)
+    X[5] = 3.25  # constant row: sd = 0 -> z = 0 for every sample (tie group at zero)
+    X[6] = X[7]  # duplicated rows -> tied z -> averaged ranks
+    G = synth.genesets_numpy(P, S, seed=36, size_cap=(5, 150))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    assert rel_err(pb.replaid_gsva(Xg, Gg, ctx=gpu_ctx).mat, O.replaid_gsva(Xo, Go).mat) < 1e-9
+    assert rel_err(pb.replaid_gsva(Xg, Gg, tau=0.5, ctx=gpu_ctx).mat, O.replaid_gsva(Xo, Go, tau=0.5).mat) < 1e-9
+    with pytest.raises(ValueError):
+        pb.replaid_gsva(Xg, Gg, rowtf="nope", ctx=gpu_ctx)
+
+
 # ---- ranking: bit-exact, adversarial -----------------------------------------------------------
 @pytest.mark.parametrize("ties", ["average", "min", "max"])
 @pytest.mark.parametrize("signed", [False, True])

@@ -26,6 +26,7 @@ def test_r_wrappers_keep_reference_signatures():
                 "replaid.scse <- function(X, matG, removeLog2 = NULL, scoreMean = FALSE)",
                 "replaid.sing <- function(X, matG)", "replaid.ssgsea <- function(X, matG, alpha = 0)",
                 "replaid.ucell <- function(X, matG, rmax = 1500)",
-                "replaid.aucell <- function(X, matG, aucMaxRank = ceiling(0.05 * nrow(X)))"]:
+                "replaid.aucell <- function(X, matG, aucMaxRank = ceiling(0.05 * nrow(X)))",
+                'replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1])']:
         assert sig in src, sig
     assert '[plaid] ERROR. No overlapping features.' in src
