@@ -26,6 +26,45 @@ constexpr unsigned long long ZERO_KEY = 0x8000000000000000ull;
 __device__ __forceinline__ int digit_shift(int d) { return d < 5 ? 53 - 11 * d : 0; }
 __device__ __forceinline__ int digit_bits(int d) { return d < 5 ? 11 : 9; }
 
+
+// Cooperative search of the histogram bin that holds rank k: every thread sums nb/NT consecutive
+// bins, warp 0 scans the NT partial sums and walks the winning group.  All NT threads must call.
+struct BinHit { int bin; unsigned before, count; };
+__device__ BinHit find_bin(const unsigned* __restrict__ hist, int nb, unsigned k, unsigned* __restrict__ part,
+                           BinHit* __restrict__ slot) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int per = nb / NT;  // 8 (2048 bins) or 2 (512 bins)
+  unsigned sum = 0;
+  for (int i = 0; i < per; ++i) sum += hist[tid * per + i];
+  part[tid] = sum;
+  __syncthreads();
+  if (tid < 32) {
+    unsigned loc = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) loc += part[lane * (NT / 32) + i];
+    unsigned incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned hit = __ballot_sync(FULL, k < incl);
+    const int l = hit ? __ffs(hit) - 1 : 31;
+    if (lane == l) {
+      unsigned before = incl - loc;
+      int g = lane * (NT / 32);
+      while (g < lane * (NT / 32) + NT / 32 - 1 && k >= before + part[g]) before += part[g++];
+      int b = g * per;
+      while (b < g * per + per - 1 && k >= before + hist[b]) before += hist[b++];
+      slot->bin = b;
+      slot->before = before;
+      slot->count = hist[b];
+    }
+  }
+  __syncthreads();
+  return *slot;
+}
+
 struct StatsSmem {
   unsigned hist[NTGT][NBIN];
   unsigned long long cand[NTGT][CAND];
@@ -40,53 +79,35 @@ struct StatsSmem {
   unsigned long long red_k[NT / 32];
   unsigned nnan, nzero, nneg;
   unsigned long long minkey;
+  unsigned part[NT];
+  BinHit hit;
 };
 
-// One warp finds, for target g, the bin of hist[g] (digit d) that holds rank k[g].
+// All threads: the bin of hist[g] (digit d) that holds rank k[g]; updates prefix / k / cnt / depth.
 __device__ void pick_bin(StatsSmem& s, int g, int d) {
-  const int lane = threadIdx.x & 31;
-  const int nb = 1 << digit_bits(d);
-  const unsigned k = s.k[g];
-  unsigned base = 0;
-  int found = -1;
-  unsigned before = 0, inbin = 0;
-  for (int b0 = 0; b0 < nb && found < 0; b0 += 32) {
-    const unsigned c = s.hist[g][b0 + lane];
-    unsigned incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const unsigned tot = __shfl_sync(FULL, incl, 31);
-    if (k < base + tot) {
-      const unsigned hit = __ballot_sync(FULL, k < base + incl);
-      const int l = __ffs(hit) - 1;
-      found = b0 + l;
-      before = base + __shfl_sync(FULL, incl - c, l);
-      inbin = __shfl_sync(FULL, c, l);
-    }
-    base += tot;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    s.prefix[g] |= (unsigned long long)found << digit_shift(d);
-    s.k[g] = k - before;
-    s.cnt[g] = inbin;
+  const BinHit h = find_bin(s.hist[g], 1 << digit_bits(d), s.k[g], s.part, &s.hit);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.prefix[g] |= (unsigned long long)h.bin << digit_shift(d);
+    s.k[g] -= h.before;
+    s.cnt[g] = h.count;
     s.depth[g] = d + 1;
   }
-  __syncwarp();
+  __syncthreads();
 }
 
+// cols == nullptr: columns 0..N-1; else the N columns listed in cols (the fast path's rejects)
 __global__ void __launch_bounds__(NT) k_colstats(const double* __restrict__ x, int64_t ld, int32_t S,
-                                                 int64_t N, double* __restrict__ med_all,
+                                                 int64_t N, const int64_t* __restrict__ cols,
+                                                 double* __restrict__ med_all,
                                                  double* __restrict__ med_nz,
                                                  double* __restrict__ colmin) {
   extern __shared__ unsigned char smem_raw[];
   StatsSmem& s = *reinterpret_cast<StatsSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+  for (int64_t it = blockIdx.x; it < N; it += gridDim.x) {
+    const int64_t j = cols ? cols[it] : it;
     const double* __restrict__ c = x + j * ld;
 
     // ---- pass 1: top-digit histogram + NaN / zero counts + min -------------------------
@@ -178,8 +199,8 @@ __global__ void __launch_bounds__(NT) k_colstats(const double* __restrict__ x, i
       if (s.active[g])
         for (int i = tid; i < NBIN; i += NT) s.hist[g][i] = s.hist[0][i];
     __syncthreads();
-    if (wid < NTGT && s.active[wid]) pick_bin(s, wid, 0);
-    __syncthreads();
+    for (int g = 0; g < NTGT; ++g)
+      if (s.active[g]) pick_bin(s, g, 0);
 
     // ---- refine digit by digit while a bucket is large (a target that stops never resumes) --
     for (int d = 1; d < NDIG; ++d) {
@@ -210,8 +231,8 @@ __global__ void __launch_bounds__(NT) k_colstats(const double* __restrict__ x, i
           if (ref[g] && hi == pf[g]) atomicAdd(&s.hist[g][bin], 1u);
       }
       __syncthreads();
-      if (wid < NTGT && ref[wid]) pick_bin(s, wid, d);
-      __syncthreads();
+      for (int g = 0; g < NTGT; ++g)
+        if (ref[g]) pick_bin(s, g, d);
     }
 
     // ---- collect the candidates of every unfinished target and rank them directly ---------
@@ -271,6 +292,345 @@ __global__ void __launch_bounds__(NT) k_colstats(const double* __restrict__ x, i
       med_all[j] = ma;
       med_nz[j] = mz;
       colmin[j] = nvalid > 0 ? value_of(s.minkey) : INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: ONE pass over the column.  A strided sample of 1024 keys is sorted in shared memory and
+// gives, for each of the two medians, a bracket [lo, hi] of sample order statistics +-2.5 sigma around
+// the wanted quantile.  The single full pass counts keys below lo / equal to lo / equal to hi and
+// collects the keys strictly inside (lo, hi) in shared memory (a few % of the column); once the exact
+// counts are known the wanted ranks are located in {==lo | inside | ==hi} and selected exactly by a
+// radix select over the collected keys.  Any column whose ranks fall outside the bracket (p ~ 1 %)
+// or whose candidates overflow is flagged and redone by the three-pass kernel above: exactness never
+// depends on the sample.
+constexpr int SAMP = 1024;
+constexpr int WCAP = 416;             // candidate slots per warp and bracket (expected ~300)
+constexpr int CCAP = WCAP * (NT / 32); // candidate slots per bracket
+
+struct Stats2Smem {
+  union {  // the sorted sample is dead once the brackets are known
+    unsigned long long samp[SAMP];
+    unsigned hist[2][NBIN];
+  };
+  unsigned long long cand[2][CCAP];  // [bracket][warp][WCAP]: every warp appends to its own segment
+  unsigned wcnt[2][NT / 32];
+  unsigned long long lo[2], hi[2];
+  unsigned below[2], eqlo[2], eqhi[2], ncand[2];
+  unsigned nnan, nzero, nneg;
+  unsigned long long minkey;
+  unsigned long long res[2][2];
+  int ok[2];
+  // scratch of the list select
+  unsigned long long prefix[2];
+  unsigned k[2], cnt[2];
+  int depth[2];
+  unsigned nsmall;
+  unsigned long long small[64];
+  unsigned part[NT];
+  BinHit hit;
+};
+
+__device__ void sort_sample(unsigned long long* k, int n) {  // n = power of two, all threads
+  for (int size = 2; size <= n; size <<= 1) {
+    const int hs = size >> 1;
+    for (int q = threadIdx.x; q < n / 2; q += blockDim.x) {
+      const int o = q & (hs - 1), base = (q & ~(hs - 1)) << 1;
+      const int i = base + o, l = base + size - 1 - o;
+      const unsigned long long a = k[i], b = k[l];
+      if (a > b) { k[i] = b; k[l] = a; }
+    }
+    __syncthreads();
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+      for (int q = threadIdx.x; q < n / 2; q += blockDim.x) {
+        const int i = ((q & ~(stride - 1)) << 1) | (q & (stride - 1)), l = i + stride;
+        const unsigned long long a = k[i], b = k[l];
+        if (a > b) { k[i] = b; k[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exact selection of ranks ka <= kb (kb - ka <= 1) among n keys in shared memory (radix, 11-bit digits);
+// every key lies in (klo, khi), so the digits klo and khi share are decided up front
+__device__ void select_from_list(Stats2Smem& s, const unsigned long long* list, const unsigned* wcnt, unsigned ntot,
+                                 unsigned ka, unsigned kb, unsigned long long klo, unsigned long long khi,
+                                 unsigned long long* out2) {
+  const int tid = threadIdx.x;
+  const unsigned n = CCAP;  // slots; slot i is live iff (i % WCAP) < wcnt[i / WCAP]
+  auto live = [&](unsigned i) { return (i % WCAP) < wcnt[i / WCAP]; };
+  int d0 = 0;
+  while (d0 < NDIG && (klo >> digit_shift(d0)) == (khi >> digit_shift(d0))) ++d0;
+  if (tid == 0) {
+    const unsigned long long common = d0 > 0 ? (klo >> digit_shift(d0 - 1)) << digit_shift(d0 - 1) : 0ull;
+    s.prefix[0] = s.prefix[1] = common;
+    s.k[0] = ka; s.k[1] = kb;
+    s.cnt[0] = s.cnt[1] = ntot;
+    s.depth[0] = s.depth[1] = d0;
+  }
+  __syncthreads();
+  for (int d = d0; d < NDIG; ++d) {
+    const bool r0 = s.cnt[0] > 32, r1 = s.cnt[1] > 32;
+    if (!r0 && !r1) break;
+    const int sh = digit_shift(d), nb = 1 << digit_bits(d);
+    const int psh = d > 0 ? digit_shift(d - 1) : 63;
+    const unsigned long long p0 = d > 0 ? s.prefix[0] >> psh : 0, p1 = d > 0 ? s.prefix[1] >> psh : 0;
+    __syncthreads();
+    for (int i = tid; i < nb; i += NT) { s.hist[0][i] = 0; s.hist[1][i] = 0; }
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += NT) {
+      if (!live(i)) continue;
+      const unsigned long long key = list[i];
+      const unsigned long long hi = d > 0 ? key >> psh : 0;
+      const unsigned bin = (unsigned)(key >> sh) & (unsigned)(nb - 1);
+      if (r0 && hi == p0) atomicAdd(&s.hist[0][bin], 1u);
+      if (r1 && hi == p1) atomicAdd(&s.hist[1][bin], 1u);
+    }
+    __syncthreads();
+    for (int g = 0; g < 2; ++g) {
+      if (!(g == 0 ? r0 : r1)) continue;
+      const BinHit h = find_bin(s.hist[g], nb, s.k[g], s.part, &s.hit);
+      __syncthreads();
+      if (tid == 0) {
+        s.prefix[g] |= (unsigned long long)h.bin << sh;
+        s.k[g] -= h.before;
+        s.cnt[g] = h.count;
+        s.depth[g] = d + 1;
+      }
+      __syncthreads();
+    }
+  }
+  // finish each target by direct ranking inside its bucket (<= 32 keys, or a fully decided key)
+  for (int g = 0; g < 2; ++g) {
+    if (s.depth[g] == NDIG) {
+      if (tid == 0) out2[g] = s.prefix[g];
+      __syncthreads();
+      continue;
+    }
+    const int psh = s.depth[g] > 0 ? digit_shift(s.depth[g] - 1) : 63;
+    const unsigned long long pf = s.depth[g] > 0 ? s.prefix[g] >> psh : 0;
+    if (tid == 0) s.nsmall = 0;
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += NT) {
+      if (!live(i)) continue;
+      const unsigned long long mine = list[i];
+      if ((s.depth[g] > 0 ? mine >> psh : 0) != pf) continue;
+      const unsigned q = atomicAdd(&s.nsmall, 1u);
+      if (q < 64) s.small[q] = mine;
+    }
+    __syncthreads();
+    const unsigned m = min(s.nsmall, 64u);
+    if ((unsigned)tid < m) {
+      const unsigned long long mine = s.small[tid];
+      unsigned r = 0;
+      for (unsigned u = 0; u < m; ++u) {
+        const unsigned long long o = s.small[u];
+        r += (o < mine) || (o == mine && u < (unsigned)tid);
+      }
+      if (r == s.k[g]) out2[g] = mine;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__ x, int64_t ld, int32_t S, int64_t N,
+                                                      double* __restrict__ med_all, double* __restrict__ med_nz,
+                                                      double* __restrict__ colmin, int* __restrict__ fail_count,
+                                                      int64_t* __restrict__ fail_list) {
+  extern __shared__ unsigned char smem_raw2[];
+  Stats2Smem& s = *reinterpret_cast<Stats2Smem*>(smem_raw2);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+    const double* __restrict__ c = x + j * ld;
+    // ---- sample ----
+    for (int i = tid; i < SAMP; i += NT) {
+      const int pos = (int)(((int64_t)i * S) / SAMP);
+      const double v = c[pos];
+      s.samp[i] = (v != v) ? ~0ull : key_of(v);
+    }
+    if (tid == 0) {
+      s.nnan = s.nzero = s.nneg = 0;
+      s.minkey = ~0ull;
+      for (int g = 0; g < 2; ++g) { s.below[g] = s.eqlo[g] = s.eqhi[g] = s.ncand[g] = 0; s.ok[g] = 1; }
+    }
+    __syncthreads();
+    sort_sample(s.samp, SAMP);
+    if (tid == 0) {
+      // valid sample entries [0, mv); zero block [zs, ze)
+      int mv = SAMP;
+      {  // NaN keys (~0) sorted last
+        int lo = 0, hi = SAMP;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.samp[mid] != ~0ull) lo = mid + 1; else hi = mid; }
+        mv = lo;
+      }
+      int zs, ze;
+      {
+        int lo = 0, hi = mv;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.samp[mid] < ZERO_KEY) lo = mid + 1; else hi = mid; }
+        zs = lo;
+        hi = mv;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.samp[mid] <= ZERO_KEY) lo = mid + 1; else hi = mid; }
+        ze = lo;
+      }
+      // bracket g = 0: median of all valid values; g = 1: median of the non-zero values
+      for (int g = 0; g < 2; ++g) {
+        const int mcount = g == 0 ? mv : mv - (ze - zs);
+        if (mcount < 48) {  // too few sample points: take everything (the candidate cap decides)
+          s.lo[g] = key_of(-INFINITY);
+          s.hi[g] = key_of(INFINITY);
+          continue;
+        }
+        const double mid = 0.5 * (double)(mcount - 1);
+        const double delta = 1.25 * sqrt((double)mcount) + 2.0;  // 2.5 sigma of a binomial(m, 1/2) rank
+        int a = (int)floor(mid - delta), b = (int)ceil(mid + delta);
+        unsigned long long klo = key_of(-INFINITY), khi = key_of(INFINITY);
+        if (a >= 0) {
+          if (g == 1 && a >= zs) a += ze - zs;
+          klo = s.samp[a];
+        }
+        if (b <= mcount - 1) {
+          if (g == 1 && b >= zs) b += ze - zs;
+          khi = s.samp[b];
+        }
+        s.lo[g] = klo;
+        s.hi[g] = khi;
+      }
+    }
+    __syncthreads();
+    // brackets as doubles: one DSETP per test instead of a 64-bit key compare; keys are only built
+    // for the few rows that land inside a bracket
+    const double lo0 = value_of(s.lo[0]), hi0 = value_of(s.hi[0]), lo1 = value_of(s.lo[1]), hi1 = value_of(s.hi[1]);
+    // ---- the one full pass ----
+    unsigned nnan = 0, nzero = 0, nneg = 0, bel0 = 0, bel1 = 0, el0 = 0, el1 = 0, eh0 = 0, eh1 = 0;
+    double minv = INFINITY;
+    unsigned wc0 = 0, wc1 = 0;  // this warp's candidate counts (warp-uniform)
+    unsigned long long* __restrict__ seg0 = s.cand[0] + wid * WCAP;
+    unsigned long long* __restrict__ seg1 = s.cand[1] + wid * WCAP;
+    constexpr int UNR = 8;  // loads of 8 rows are issued before any of them is consumed
+    for (int l0 = 0; l0 < S; l0 += NT * UNR) {
+      double vv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int l = l0 + u * NT + tid;
+        vv[u] = (l < S) ? __ldcs(c + l) : INFINITY;  // +inf padding is subtracted below
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const double v = vv[u];
+        const bool isnan_ = v != v;
+        const bool isz = v == 0.0;
+        nnan += isnan_;
+        nzero += isz;
+        nneg += v < 0.0;
+        minv = fmin(minv, v);
+        const bool lt0 = v < lo0, gt0 = v > hi0;
+        const bool lt1 = v < lo1, gt1 = v > hi1;
+        bel0 += lt0;
+        bel1 += lt1 && !isz;
+        const bool mid0 = !(lt0 || gt0 || isnan_);
+        const bool mid1 = !(lt1 || gt1 || isnan_ || isz);
+        // bracket ends and candidates; every warp appends to its own segment: no atomics, no shuffles
+        const bool live = (l0 + u * NT + tid) < S;
+        el0 += mid0 && v == lo0;
+        eh0 += live && mid0 && v == hi0 && hi0 != lo0;
+        el1 += mid1 && v == lo1;
+        eh1 += live && mid1 && v == hi1 && hi1 != lo1;
+        const bool in0 = live && mid0 && v > lo0 && v < hi0;
+        const bool in1 = live && mid1 && v > lo1 && v < hi1;
+        const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
+        if (m0 | m1) {
+          const unsigned long long key = key_of(v);
+          const unsigned p0 = wc0 + __popc(m0 & lt), p1 = wc1 + __popc(m1 & lt);
+          if (in0 && p0 < WCAP) seg0[p0] = key;
+          if (in1 && p1 < WCAP) seg1[p1] = key;
+          wc0 += __popc(m0);
+          wc1 += __popc(m1);
+        }
+      }
+    }
+    if (lane == 0) {
+      s.wcnt[0][wid] = wc0;
+      s.wcnt[1][wid] = wc1;
+      atomicAdd(&s.ncand[0], min(wc0, (unsigned)WCAP));
+      atomicAdd(&s.ncand[1], min(wc1, (unsigned)WCAP));
+      if (wc0 > WCAP || wc1 > WCAP) s.ok[0] = 0;  // segment overflow: exact fallback
+    }
+    // rows past the end were loaded as +inf: they are neither NaN, zero nor negative, never below a bracket,
+    // and only count as "== hi" when hi is +inf, which the `live` test above already excludes
+    unsigned long long mink = minv == INFINITY ? ~0ull : key_of(minv);
+    // block totals
+    auto wsum = [&](unsigned v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      return v;
+    };
+    nnan = wsum(nnan); nzero = wsum(nzero); nneg = wsum(nneg);
+    bel0 = wsum(bel0); bel1 = wsum(bel1); el0 = wsum(el0); el1 = wsum(el1); eh0 = wsum(eh0); eh1 = wsum(eh1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long mk = __shfl_xor_sync(FULL, mink, o);
+      mink = mk < mink ? mk : mink;
+    }
+    if (lane == 0) {
+      atomicAdd(&s.nnan, nnan); atomicAdd(&s.nzero, nzero); atomicAdd(&s.nneg, nneg);
+      atomicAdd(&s.below[0], bel0); atomicAdd(&s.below[1], bel1);
+      atomicAdd(&s.eqlo[0], el0); atomicAdd(&s.eqlo[1], el1);
+      atomicAdd(&s.eqhi[0], eh0); atomicAdd(&s.eqhi[1], eh1);
+      atomicMin(&s.minkey, mink);
+    }
+    __syncthreads();
+    // ---- locate the wanted ranks ----
+    const unsigned nvalid = (unsigned)S - s.nnan;
+    const unsigned cnt[2] = {nvalid, nvalid - s.nzero};
+    bool good = true;
+    for (int g = 0; g < 2; ++g) {
+      if (cnt[g] == 0) continue;
+      const unsigned ka = (cnt[g] - 1) / 2, kb = cnt[g] / 2;
+      const unsigned b = s.below[g], e1 = b + s.eqlo[g], nin = s.ncand[g], e2 = e1 + nin, e3 = e2 + s.eqhi[g];
+      if (!s.ok[0] || nin > CCAP || ka < b || kb >= e3) {
+        good = false;
+        continue;
+      }
+      // both ranks inside {==lo | inside | ==hi}
+      const bool a_in = ka >= e1 && ka < e2, b_in = kb >= e1 && kb < e2;
+      if (a_in || b_in) {
+        const unsigned qa = a_in ? ka - e1 : kb - e1, qb = b_in ? kb - e1 : ka - e1;
+        select_from_list(s, s.cand[g], s.wcnt[g], nin, qa < qb ? qa : qb, qa < qb ? qb : qa, s.lo[g], s.hi[g], s.res[g]);
+        // res[g][0] = smaller requested rank, res[g][1] = larger
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long ra, rb;
+        if (ka < e1) ra = s.lo[g]; else if (ka < e2) ra = s.res[g][0]; else ra = s.hi[g];
+        if (kb < e1) rb = s.lo[g]; else if (kb < e2) rb = (a_in ? s.res[g][1] : s.res[g][0]); else rb = s.hi[g];
+        s.res[g][0] = ra;
+        s.res[g][1] = rb;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (!good) {
+        const int slot = atomicAdd(fail_count, 1);
+        fail_list[slot] = j;
+      } else {
+        double ma = nan(""), mz = 0.0;
+        if (cnt[0] > 0) {
+          const double a = value_of(s.res[0][0]), b = value_of(s.res[0][1]);
+          ma = (cnt[0] & 1u) ? a : (a + b) / 2.0;
+        }
+        if (cnt[1] > 0) {
+          const double a = value_of(s.res[1][0]), b = value_of(s.res[1][1]);
+          mz = (cnt[1] & 1u) ? a : (a + b) / 2.0;
+        }
+        med_all[j] = ma;
+        med_nz[j] = mz;
+        colmin[j] = nvalid > 0 ? value_of(s.minkey) : INFINITY;
+      }
     }
     __syncthreads();
   }
@@ -357,15 +717,51 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
     cudaError_t e = cudaFuncSetAttribute(k_colstats, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(StatsSmem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_colstats_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats2Smem));
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t grid = (int64_t)sms * 4;  // 4 x 40 KB of shared memory per SM
+  if (S < 4 * SAMP) {  // short columns: the three-pass kernel is as cheap as sampling
+    int64_t grid = (int64_t)sms * 4;
+    if (grid > N) grid = N;
+    k_colstats<<<(unsigned)grid, NT, sizeof(StatsSmem), st>>>(x, ld, S, N, nullptr, med_all, med_nz, colmin);
+    return cudaGetLastError();
+  }
+  // single-pass kernel, then the exact three-pass kernel on whatever it rejected
+  int* d_fail = nullptr;
+  int64_t* d_list = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_fail, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMallocAsync(&d_list, (size_t)N * sizeof(int64_t), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast, NT, sizeof(Stats2Smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sms * per_sm;
   if (grid > N) grid = N;
-  k_colstats<<<(unsigned)grid, NT, sizeof(StatsSmem), st>>>(x, ld, S, N, med_all, med_nz, colmin);
-  return cudaGetLastError();
+  k_colstats_fast<<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int nfail = 0;
+  e = cudaMemcpyAsync(&nfail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  if (nfail > 0) {
+    int64_t g2 = (int64_t)sms * 4;
+    if (g2 > nfail) g2 = nfail;
+    k_colstats<<<(unsigned)g2, NT, sizeof(StatsSmem), st>>>(x, ld, S, nfail, d_list, med_all, med_nz, colmin);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  cudaFreeAsync(d_fail, st);
+  cudaFreeAsync(d_list, st);
+  return cudaSuccess;
 }
 
 cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, int64_t j0, int64_t j1,

@@ -196,6 +196,27 @@ def test_normalize_medians_edge_cases(gpu_ctx):
     assert rel_err(pb.normalize_medians(e, ctx=gpu_ctx), O.normalize_medians(e)) < 1e-13
 
 
+def test_normalize_medians_long_columns_single_pass_path(gpu_ctx):
+    """columns >= 4096 rows go through the sampled single-pass kernel (+ exact fallback): adversarial shapes"""
+    rng = np.random.default_rng(14)
+    S, N = 9000, 24
+    x = np.abs(rng.normal(size=(S, N))) + 0.1
+    x[rng.random(x.shape) < 0.3] = 0.0          # many zeros -> the two medians differ a lot
+    x[:, 1] = 0.0                                # all-zero column
+    x[:, 2] = 4.5                                # constant column (every candidate ties)
+    x[:, 3] = np.round(x[:, 3], 1)               # heavy ties around the median
+    x[:, 4] = 0.0; x[:40, 4] = rng.random(40)    # almost all zero: few non-zeros
+    x[::7, 5] = np.nan                           # NaNs dropped
+    x[:, 6] = rng.normal(size=S) * 10.0 ** rng.integers(-250, 250, size=S)  # wild exponents, negatives
+    x[:, 7] = np.sort(x[:, 7])                   # sorted column: a strided sample is still fine
+    x[:, 8] = np.where(np.arange(S) % 2 == 0, 1.0, 2.0)  # two values, even count -> mean of middles
+    assert rel_err(pb.normalize_medians(x, ctx=gpu_ctx), O.normalize_medians(x)) < 1e-13
+    for iz in (False, True):
+        assert rel_err(pb.normalize_medians(x, ignore_zero=iz, ctx=gpu_ctx), O.normalize_medians(x, ignore_zero=iz)) < 1e-13
+    y = rng.normal(size=(30000, 6))              # C4-length columns, no zeros, negatives
+    assert rel_err(pb.normalize_medians(y, ctx=gpu_ctx), O.normalize_medians(y)) < 1e-13
+
+
 # ---- reference edge cases ------------------------------------------------------------------------
 def test_no_overlap_returns_none(gpu_ctx):
     X = synth.sparse_x_numpy(50, 4, seed=1, density=0.3)
