@@ -66,24 +66,42 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
     }
     __syncthreads();
 
-    // ---- gather: one warp per set, lanes = columns -----------------------------------------
+    // ---- gather: one warp per group of GS consecutive sets, lanes = columns ---------------------
+    // The member lists of consecutive sets are contiguous, so a group is ONE stream of 4-member
+    // chunks; chunks are fetched 4..8 ahead of their use (the L2 latency of the list loads was the
+    // top stall), set boundaries are multiples of a chunk and are held one per lane.
     const char* __restrict__ xlane = reinterpret_cast<const char*>(Xs) + lane * 8;
+    const uint4* __restrict__ ids = reinterpret_cast<const uint4*>(p.didx);
+    const uint4 zrow = make_uint4((unsigned)K * 256u, (unsigned)K * 256u, (unsigned)K * 256u, (unsigned)K * 256u);
     for (int s0 = w * GS; s0 < p.S; s0 += GW * GS) {
       const int ns = min(GS, p.S - s0);
-      for (int i = 0; i < ns; ++i) {
-        const uint32_t b = p.dptr[s0 + i], e = p.dptr[s0 + i + 1];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const uint4* __restrict__ ids = reinterpret_cast<const uint4*>(p.didx + b);  // byte offsets of rows
-        const int n4 = (int)((e - b) >> 2);
-#pragma unroll 2
-        for (int m = 0; m < n4; ++m) {
-          const uint4 q = __ldg(ids + m);
-          a0 += *reinterpret_cast<const double*>(xlane + q.x);
-          a1 += *reinterpret_cast<const double*>(xlane + q.y);
-          a2 += *reinterpret_cast<const double*>(xlane + q.z);
-          a3 += *reinterpret_cast<const double*>(xlane + q.w);
+      const uint32_t bnd = (lane <= ns) ? (p.dptr[s0 + lane] >> 2) : 0u;  // chunk index where set lane starts
+      const uint32_t cbeg = __shfl_sync(FULL, bnd, 0), cend = __shfl_sync(FULL, bnd, ns);
+      int i = 0;
+      uint32_t nextb = __shfl_sync(FULL, bnd, 1);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      uint4 q[4], nq[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) q[c] = (cbeg + c < cend) ? __ldg(ids + cbeg + c) : zrow;
+      for (uint32_t m = cbeg; m < cend || i < ns; m += 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nq[c] = (m + 4 + c < cend) ? __ldg(ids + m + 4 + c) : zrow;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          while (i < ns && m + c == nextb) {  // set i is complete (possibly empty): stage its 32 column sums
+            stw[lane * GPAD + i] = (a0 + a1) + (a2 + a3);
+            a0 = a1 = a2 = a3 = 0.0;
+            ++i;
+            nextb = __shfl_sync(FULL, bnd, min(i + 1, 31));
+          }
+          const uint4 qq = q[c];
+          a0 += *reinterpret_cast<const double*>(xlane + qq.x);
+          a1 += *reinterpret_cast<const double*>(xlane + qq.y);
+          a2 += *reinterpret_cast<const double*>(xlane + qq.z);
+          a3 += *reinterpret_cast<const double*>(xlane + qq.w);
         }
-        stw[lane * GPAD + i] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = nq[c];
       }
       __syncwarp();
       // transposed write-out: 4 columns x 8 consecutive sets (64 contiguous bytes each) per store
