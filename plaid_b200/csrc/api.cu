@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -152,24 +153,36 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
     if (gK <= 0) return fail(c, PLAIDGPU_ERR_CUDA, "no shared memory for the gather tile");
     gblocks = (P + gK - 1) / gK;
   } else if (Kmax > 0 && S >= 1024 && nnzm >= 100000) {
-    // the K highest-degree rows: in single-cell data these are the ubiquitous genes, i.e. the rows
-    // of X that are nearly dense and carry most of the adds
+    // blocks of the highest-degree rows: in single-cell data these are the ubiquitous genes, i.e. the
+    // rows of X that are nearly dense and carry most of the adds.  Block 0 = ranks [0, K), block 1 =
+    // ranks [K, 2K) ... (each further block costs one more read-modify-write of the output)
+    int want_blocks = 1;  // measured on C4: a 2nd / 3rd block costs more (extra pass over the output) than it saves
+    if (const char* e = getenv("PLAIDGPU_GATHER_BLOCKS")) want_blocks = std::max(0, std::min(8, atoi(e)));
     std::vector<int32_t> order((size_t)P);
     for (int32_t r = 0; r < P; ++r) order[r] = r;
-    const int32_t want = std::min<int32_t>(Kmax, P);
+    const int32_t want = (int32_t)std::min<int64_t>((int64_t)Kmax * want_blocks, P);
     std::partial_sort(order.begin(), order.begin() + want, order.end(),
                       [&](int32_t x, int32_t y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
     int32_t k = 0;
     while (k < want && deg[order[k]] > 0) ++k;
-    gK = ((k + 31) / 32) * 32;
-    if (gK > Kmax) gK = Kmax;
-    if (k > gK) k = gK;
-    if (k >= 32) {
-      dmap.assign((size_t)P, 0xFFFFu);
-      std::vector<int32_t> sel(order.begin(), order.begin() + k);
-      std::sort(sel.begin(), sel.end());  // local ids ascend with the row index (reference sum order)
-      for (int32_t i = 0; i < k; ++i) dmap[sel[i]] = (uint16_t)i;
+    gK = Kmax;
+    gblocks = k / Kmax;                       // full blocks only, except that a single partial block of
+    if (gblocks == 0 && k >= 32) {            // >= 32 rows is still worth a gather pass
       gblocks = 1;
+      gK = std::min(Kmax, ((k + 31) / 32) * 32);
+    }
+    if (gblocks > 0) {
+      blk_of_row.assign((size_t)P, -1);
+      dmap.assign((size_t)P * gblocks, 0xFFFFu);
+      for (int32_t b = 0; b < gblocks; ++b) {
+        const int32_t lo = b * gK, hi = std::min(k, (b + 1) * gK);
+        std::vector<int32_t> sel(order.begin() + lo, order.begin() + hi);
+        std::sort(sel.begin(), sel.end());  // local ids ascend with the row index (reference sum order)
+        for (size_t i = 0; i < sel.size(); ++i) {
+          dmap[(size_t)b * P + sel[i]] = (uint16_t)i;
+          blk_of_row[sel[i]] = b;
+        }
+      }
     } else {
       gK = 0;
     }
@@ -186,7 +199,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         const int32_t r = g2x[c->Gi[q]];
         if (r < 0) continue;
         if (dense) ++cnt[(size_t)(r / gK) * S + s];
-        else if (dmap[r] != 0xFFFFu) ++cnt[s];
+        else if (blk_of_row[r] >= 0) ++cnt[(size_t)blk_of_row[r] * S + s];
       }
     uint64_t off = 0;
     for (int32_t b = 0; b < gblocks; ++b) {
@@ -207,7 +220,8 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         const int32_t r = g2x[c->Gi[q]];
         if (r < 0) continue;
         if (dense) didx[pos[(size_t)(r / gK) * S + s]++] = (uint32_t)(r % gK) * 256u;
-        else if (dmap[r] != 0xFFFFu) didx[pos[s]++] = (uint32_t)dmap[r] * 256u;
+        else if (blk_of_row[r] >= 0)
+          didx[pos[(size_t)blk_of_row[r] * S + s]++] = (uint32_t)dmap[(size_t)blk_of_row[r] * P + r] * 256u;
       }
     for (int32_t b = 0; b < gblocks; ++b)
       for (int32_t s = 0; s < S; ++s) {
@@ -222,7 +236,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   std::vector<uint16_t> idx(1);
   int64_t nnz_scatter = 0;
   if (!dense) {
-    auto in_block = [&](int32_t r) { return !dmap.empty() && dmap[r] != 0xFFFFu; };
+    auto in_block = [&](int32_t r) { return !blk_of_row.empty() && blk_of_row[r] >= 0; };
     std::vector<uint32_t> rowcnt((size_t)P + 1, 0);
     for (int32_t r = 0; r < P; ++r) rowcnt[r + 1] = rowcnt[r] + (in_block(r) ? 0u : deg[r]);
     nnz_scatter = rowcnt[P];
@@ -750,7 +764,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     g.r0 = p.r0;
     g.P = c->P;
     g.N = c->N;
-    g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>();
+
     g.K = c->gK;
     g.didx = c->d_didx.as<uint32_t>();
     g.inv = p.inv;
@@ -764,6 +778,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     g.ld = c->S;
     for (int32_t b = 0; b < c->gblocks; ++b) {
       g.g0 = b * c->gK;
+      g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>() + (size_t)b * c->P;
       g.dptr = c->d_dptr.as<uint32_t>() + (size_t)b * (c->S + 1);
       g.accumulate = b > 0;
       g.final = c->dense && (b == c->gblocks - 1);  // sparse X: the scatter pass finishes the scores
