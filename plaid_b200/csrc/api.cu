@@ -909,8 +909,109 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
   return PLAIDGPU_OK;
 }
 
+// Column-chunked scoring for host input / host output when the S x N result does not fit the device
+// (e.g. 30k sets x 1M cells = 240 GB): the same begin / compute / finish pipeline runs per chunk of
+// columns (the axis chunked_crossprod splits on, R/plaid.R:110-119).  The global scalars need all
+// columns, so a normalised call recomputes the scores: pass 1 keeps only the per-column medians,
+// pass 2 recomputes, fixes up and streams each chunk out (recomputing costs less than moving the raw
+// scores over PCIe twice).  Results are bit-identical to the un-chunked path.
+static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
+                         double* out, int64_t chunk) {
+  const int64_t N = X->N;
+  const int32_t S = c->S;
+  if (opts->scorer == PLAIDGPU_GSVA && !(opts->row_mean && opts->row_sd))
+    return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva: matrix too large for one device pass; pass row_mean / row_sd");
+  std::vector<int32_t> pbuf;
+  auto sub = [&](int64_t j0, int64_t j1, plaidgpu_matrix* M) {
+    *M = *X;
+    M->N = j1 - j0;
+    if (X->kind == PLAIDGPU_CSC) {
+      const int32_t base = X->p[j0];
+      pbuf.resize((size_t)(j1 - j0 + 1));
+      for (int64_t j = j0; j <= j1; ++j) pbuf[(size_t)(j - j0)] = X->p[j] - base;
+      M->p = pbuf.data();
+      M->i = X->i + base;
+      M->x = X->x + base;
+    } else {
+      M->x = X->x + j0 * (int64_t)X->P;
+    }
+  };
+  plaidgpu_scalars g;
+  memset(&g, 0, sizeof(g));
+  g.x_min = INFINITY;
+  g.x_max = -INFINITY;
+  g.score_min = INFINITY;
+  g.ignore_zero = -1;
+  const bool need_pre = is_rank_scorer(opts->scorer) || opts->scorer == PLAIDGPU_GSVA ||
+                        (opts->scorer == PLAIDGPU_SCSE && opts->remove_log2 < 0);
+  plaidgpu_matrix M;
+  plaidgpu_scalars loc;
+  int rc;
+  if (need_pre) {
+    for (int64_t j0 = 0; j0 < N; j0 += chunk) {
+      sub(j0, std::min(N, j0 + chunk), &M);
+      rc = plaidgpu_score_begin(c, &M, rowmap, opts, &loc);
+      if (rc) return rc;
+      g.x_min = fmin(g.x_min, loc.x_min);
+      g.x_max = fmax(g.x_max, loc.x_max);
+      g.rank_max = fmax(g.rank_max, loc.rank_max);
+    }
+  }
+  const bool norm = (opts->scorer == PLAIDGPU_PLAID && opts->normalize) || opts->scorer == PLAIDGPU_SSGSEA ||
+                    opts->scorer == PLAIDGPU_UCELL || opts->scorer == PLAIDGPU_AUCELL || opts->scorer == PLAIDGPU_GSVA;
+  if (norm) {
+    std::vector<double> ma((size_t)N), mz((size_t)N);
+    double smin = INFINITY;
+    for (int64_t j0 = 0; j0 < N; j0 += chunk) {
+      const int64_t j1 = std::min(N, j0 + chunk);
+      sub(j0, j1, &M);
+      rc = plaidgpu_score_begin(c, &M, rowmap, opts, &loc);
+      if (rc) return rc;
+      plaidgpu_scalars s = g;
+      rc = plaidgpu_score_compute(c, &s, nullptr);
+      if (rc) return rc;
+      memcpy(ma.data() + j0, c->h_med_all.data(), (size_t)(j1 - j0) * sizeof(double));
+      memcpy(mz.data() + j0, c->h_med_nz.data(), (size_t)(j1 - j0) * sizeof(double));
+      smin = fmin(smin, s.score_min);
+    }
+    rc = plaidgpu_combine_medians(opts->ignore_zero, smin, ma.data(), mz.data(), N, &g);
+    if (rc) return fail(c, rc, "combine_medians failed");
+  }
+  for (int64_t j0 = 0; j0 < N; j0 += chunk) {
+    const int64_t j1 = std::min(N, j0 + chunk);
+    sub(j0, j1, &M);
+    rc = plaidgpu_score_begin(c, &M, rowmap, opts, &loc);
+    if (rc) return rc;
+    plaidgpu_scalars s = g;
+    rc = plaidgpu_score_compute(c, &s, nullptr);
+    if (rc) return rc;
+    s.ignore_zero = g.ignore_zero;
+    s.med_mean = g.med_mean;
+    rc = plaidgpu_score_finish(c, &s, out + j0 * (int64_t)S);
+    if (rc) return rc;
+  }
+  return PLAIDGPU_OK;
+}
+
 int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
                    double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !opts) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  // host in / host out larger than the device can hold -> column chunks
+  if (c->have_g && X->location == PLAIDGPU_HOST && opts->out_location == PLAIDGPU_HOST && X->N > 1) {
+    CK(cudaSetDevice(c->device));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    double budget = 0.45 * (double)free_b + (double)c->b_raw.cap;  // raw scores; X, ranks and slack share the rest
+    if (const char* e = getenv("PLAIDGPU_MAX_OUT_BYTES")) budget = atof(e);  // test knob
+    const double need = (double)c->S * (double)X->N * 8.0;
+    if (need > budget) {
+      int64_t chunk = (int64_t)(budget / ((double)c->S * 8.0));
+      if (chunk < 1) chunk = 1;
+      if (chunk > 32) chunk = (chunk / 32) * 32;
+      return score_chunked(c, X, rowmap, opts, out, chunk);
+    }
+  }
   plaidgpu_scalars s;
   int rc = plaidgpu_score_begin(c, X, rowmap, opts, &s);
   if (rc) return rc;

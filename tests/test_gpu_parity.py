@@ -258,6 +258,30 @@ def test_chunked_crossprod_matches(gpu_ctx):
     assert rel_err(pb.chunked_crossprod(G, X, chunk=7, ctx=gpu_ctx), O.chunked_crossprod(G, X, chunk=7)) < TOL
 
 
+def test_column_chunked_host_path_is_bit_identical(monkeypatch):
+    """outputs larger than the device budget are scored in column chunks (two passes when normalised);
+    forced here with a tiny budget: results must equal the one-pass results bit for bit"""
+    P, N, S = 1500, 203, 1100
+    X = synth.sparse_x_numpy(P, N, seed=81)
+    D = synth.dense_x_numpy(P, 67, seed=82)
+    G = synth.genesets_numpy(P, S, seed=83, size_cap=(5, 200))
+    names = synth.gene_names(P)
+    Gn = pb.NamedMatrix(G, names)
+    ctx = pb.Context(0)
+    calls = [lambda c: pb.plaid(pb.NamedMatrix(X, names), Gn, ctx=c).mat,
+             lambda c: pb.plaid(pb.NamedMatrix(X, names), Gn, stats="sum", normalize=False, ctx=c).mat,
+             lambda c: pb.plaid(pb.NamedMatrix(D, names), Gn, ctx=c).mat,
+             lambda c: pb.replaid_ucell(pb.NamedMatrix(X, names), Gn, rmax=200, ctx=c).mat,
+             lambda c: pb.replaid_ssgsea(pb.NamedMatrix(X, names), Gn, alpha=0.25, ctx=c).mat,
+             lambda c: pb.replaid_scse(pb.NamedMatrix(X, names), Gn, ctx=c).mat]
+    whole = [f(ctx) for f in calls]
+    monkeypatch.setenv("PLAIDGPU_MAX_OUT_BYTES", str(S * 8 * 40))  # 40 columns per chunk (rounded to 32)
+    parts = [f(ctx) for f in calls]
+    for a, b in zip(whole, parts):
+        assert np.array_equal(a, b)
+    assert rel_err(whole[0], O.plaid(O.Named(X, names), O.Named(G, names)).mat) < TOL
+
+
 # ---- size-independent properties at larger sizes (no oracle needed) ---------------------------------
 def test_properties_linearity_and_column_independence(gpu_ctx):
     P, N, S = 20000, 512, 30000
