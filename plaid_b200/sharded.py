@@ -116,3 +116,42 @@ def shard_columns(n_total: int, world: int, rank: int):
     base, rem = divmod(n_total, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def score_multi(ctxs, mats, rowmap: np.ndarray, opts_list, out_ptrs, n_cols):
+    """The same protocol with several contexts driven by ONE process (one context per GPU, or several
+    on one GPU): shards in column order.  This is how a single R process would use more than one GPU."""
+    lib = ctxs[0].lib
+    k = len(ctxs)
+    locs = [L.Scalars() for _ in range(k)]
+    for c, M, o, loc in zip(ctxs, mats, opts_list, locs):
+        c.check(lib.plaidgpu_score_begin(c.h, C.byref(M), rowmap.ctypes.data, C.byref(o), C.byref(loc)))
+    g = L.Scalars()
+    C.memmove(C.byref(g), C.byref(locs[0]), C.sizeof(L.Scalars))
+    g.x_min = min(l.x_min for l in locs)
+    g.x_max = max(l.x_max for l in locs)
+    g.rank_max = max(l.rank_max for l in locs)
+    scal = []
+    for c, outp in zip(ctxs, out_ptrs):
+        s = L.Scalars()
+        C.memmove(C.byref(s), C.byref(g), C.sizeof(L.Scalars))
+        c.check(lib.plaidgpu_score_compute(c.h, C.byref(s), outp))
+        scal.append(s)
+    o0 = opts_list[0]
+    if (o0.scorer in (L.SSGSEA, L.UCELL, L.AUCELL, L.GSVA)) or (o0.scorer == L.PLAID and o0.normalize):
+        mas, mzs = [], []
+        for c, n in zip(ctxs, n_cols):
+            ma = np.empty(n)
+            mz = np.empty(n)
+            c.check(lib.plaidgpu_get_col_medians(c.h, ma.ctypes.data, mz.ctypes.data))
+            mas.append(ma)
+            mzs.append(mz)
+        ga, gz = np.concatenate(mas), np.concatenate(mzs)
+        smin = min(s.score_min for s in scal)
+        for s in scal:
+            rc = lib.plaidgpu_combine_medians(int(o0.ignore_zero), smin, ga.ctypes.data, gz.ctypes.data, ga.size, C.byref(s))
+            if rc != L.OK:
+                raise L.PlaidGpuError(rc, "plaidgpu_combine_medians failed")
+    for c, s, outp in zip(ctxs, scal, out_ptrs):
+        c.check(lib.plaidgpu_score_finish(c.h, C.byref(s), outp))
+    return scal

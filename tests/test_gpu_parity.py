@@ -258,6 +258,35 @@ def test_chunked_crossprod_matches(gpu_ctx):
     assert rel_err(pb.chunked_crossprod(G, X, chunk=7, ctx=gpu_ctx), O.chunked_crossprod(G, X, chunk=7)) < TOL
 
 
+def test_sharded_protocol_is_shard_count_invariant():
+    """column shards on separate contexts (begin / compute / finish with exchanged scalars) give exactly
+    the single-context result, for 2 and 3 ragged shards (multi-GPU invariance)"""
+    from plaid_b200 import _lib as L, sharded
+    from plaid_b200.api import _matrix_struct, _opts
+    P, N, S = 1200, 101, 1500
+    X = synth.sparse_x_numpy(P, N, seed=91)
+    G = synth.genesets_numpy(P, S, seed=92, size_cap=(5, 200))
+    names = synth.gene_names(P)
+    rowmap = pb.make_rowmap(names, names)
+    ctxs = [pb.Context(0) for _ in range(3)]
+    for c in ctxs:
+        c.set_genesets(G)
+    for scorer, kw in [(L.PLAID, dict(normalize=1)), (L.UCELL, dict(rmax=150.0)), (L.SSGSEA, dict(alpha=0.0)),
+                       (L.SCSE, dict())]:
+        whole = np.empty((S, N), order="F")
+        keep = []
+        M = _matrix_struct(X, keep)
+        o = _opts(ctxs[0].lib, scorer=scorer, out_location=L.HOST, **kw)
+        ctxs[0].check(ctxs[0].lib.plaidgpu_score(ctxs[0].h, M, rowmap.ctypes.data, o, whole.ctypes.data))
+        for world in (2, 3):
+            spans = [sharded.shard_columns(N, world, r) for r in range(world)]
+            outs = [np.empty((S, hi - lo), order="F") for lo, hi in spans]
+            mats = [_matrix_struct(X[:, lo:hi], keep) for lo, hi in spans]
+            opts = [_opts(ctxs[0].lib, scorer=scorer, out_location=L.HOST, **kw) for _ in spans]
+            sharded.score_multi(ctxs[:world], mats, rowmap, opts, [a.ctypes.data for a in outs], [hi - lo for lo, hi in spans])
+            assert np.array_equal(np.concatenate(outs, axis=1), whole)
+
+
 def test_column_chunked_host_path_is_bit_identical(monkeypatch):
     """outputs larger than the device budget are scored in column chunks (two passes when normalised);
     forced here with a tiny budget: results must equal the one-pass results bit for bit"""
