@@ -259,7 +259,7 @@ def run_ours(a):
                            "l2": "inputs_exceed_l2 (X 2.1 GB + out 30 GB per GPU vs 126 MB L2; no flush needed)",
                            "timing": "K steps bracketed by barrier + cuda synchronize, max over ranks"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -374,11 +374,23 @@ def run_reference(a):
                        "cells_per_step": n},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = 1
+
+
+def _emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter that
+    writes to fd 1) was redirected to stderr at start-up"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
