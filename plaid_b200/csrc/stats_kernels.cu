@@ -505,6 +505,8 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
     // brackets as doubles: one DSETP per test instead of a 64-bit key compare; keys are only built
     // for the few rows that land inside a bracket
     const double lo0 = value_of(s.lo[0]), hi0 = value_of(s.hi[0]), lo1 = value_of(s.lo[1]), hi1 = value_of(s.hi[1]);
+    const float lo0f = __double2float_rd(lo0), hi0f = __double2float_ru(hi0);
+    const float lo1f = __double2float_rd(lo1), hi1f = __double2float_ru(hi1);
     // ---- the one full pass ----
     unsigned nnan = 0, nzero = 0, nneg = 0, bel0 = 0, bel1 = 0, el0 = 0, el1 = 0, eh0 = 0, eh1 = 0;
     double minv = INFINITY;
@@ -522,34 +524,43 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const double v = vv[u];
-        const bool isnan_ = v != v;
-        const bool isz = v == 0.0;
+        // fp32 filter (fp64 compares run on the slow pipe): rn(v) < rd(lo) implies v < lo, rn(v) > ru(hi)
+        // implies v > hi; whatever the filter cannot decide goes to the exact path below
+        const float f = __double2float_rn(v);
+        const bool isnan_ = f != f;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        const bool isz = (bits << 1) == 0ull;
         nnan += isnan_;
         nzero += isz;
-        nneg += v < 0.0;
         minv = fmin(minv, v);
-        const bool lt0 = v < lo0, gt0 = v > hi0;
-        const bool lt1 = v < lo1, gt1 = v > hi1;
+        const bool lt0 = f < lo0f, gt0 = f > hi0f;
+        const bool lt1 = f < lo1f, gt1 = f > hi1f;
         bel0 += lt0;
         bel1 += lt1 && !isz;
         const bool mid0 = !(lt0 || gt0 || isnan_);
         const bool mid1 = !(lt1 || gt1 || isnan_ || isz);
-        // bracket ends and candidates; every warp appends to its own segment: no atomics, no shuffles
-        const bool live = (l0 + u * NT + tid) < S;
-        el0 += mid0 && v == lo0;
-        eh0 += live && mid0 && v == hi0 && hi0 != lo0;
-        el1 += mid1 && v == lo1;
-        eh1 += live && mid1 && v == hi1 && hi1 != lo1;
-        const bool in0 = live && mid0 && v > lo0 && v < hi0;
-        const bool in1 = live && mid1 && v > lo1 && v < hi1;
-        const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
-        if (m0 | m1) {
-          const unsigned long long key = key_of(v);
-          const unsigned p0 = wc0 + __popc(m0 & lt), p1 = wc1 + __popc(m1 & lt);
-          if (in0 && p0 < WCAP) seg0[p0] = key;
-          if (in1 && p1 < WCAP) seg1[p1] = key;
-          wc0 += __popc(m0);
-          wc1 += __popc(m1);
+        const unsigned mm = __ballot_sync(FULL, mid0 || mid1);
+        if (mm) {
+          // exact tests for the undecided rows; every warp appends to its own segment (no atomics)
+          const bool live = (l0 + u * NT + tid) < S;
+          const bool b0 = live && mid0 && v < lo0, b1 = live && mid1 && v < lo1;  // filter inconclusive, exact says below
+          bel0 += b0;
+          bel1 += b1;
+          el0 += live && mid0 && v == lo0;
+          eh0 += live && mid0 && v == hi0 && hi0 != lo0;
+          el1 += live && mid1 && v == lo1;
+          eh1 += live && mid1 && v == hi1 && hi1 != lo1;
+          const bool in0 = live && mid0 && v > lo0 && v < hi0;
+          const bool in1 = live && mid1 && v > lo1 && v < hi1;
+          const unsigned m0 = __ballot_sync(FULL, in0), m1 = __ballot_sync(FULL, in1);
+          if (m0 | m1) {
+            const unsigned long long key = key_of(v);
+            const unsigned p0 = wc0 + __popc(m0 & lt), p1 = wc1 + __popc(m1 & lt);
+            if (in0 && p0 < WCAP) seg0[p0] = key;
+            if (in1 && p1 < WCAP) seg1[p1] = key;
+            wc0 += __popc(m0);
+            wc1 += __popc(m1);
+          }
         }
       }
     }
