@@ -81,7 +81,7 @@ struct plaidgpu_ctx {
   const int32_t* xp = nullptr;
   const int32_t* xi = nullptr;
   const double* xx = nullptr;
-  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb;
+  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb, b_fail, b_list;
   double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
   bool need_norm = false;
   std::vector<double> h_med_all, h_med_nz, h_colmin;
@@ -483,7 +483,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
                     &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
-                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb};
+                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -799,8 +799,10 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     CK(c->b_med_nz.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
     CK(c->b_colmin.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
     CK(cudaEventRecord(c->ev[2], c->stream));
+    CK(c->b_fail.reserve(sizeof(int)));
+    CK(c->b_list.reserve(std::max<int64_t>(c->N, 1) * sizeof(int64_t)));
     CK(launch_colstats(c->raw, c->S, c->S, c->N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(),
-                       c->b_colmin.as<double>(), c->stream));
+                       c->b_colmin.as<double>(), c->b_fail.as<int>(), c->b_list.as<int64_t>(), c->stream));
     c->launches += 1;
     CK(cudaEventRecord(c->ev[3], c->stream));
     c->h_med_all.resize((size_t)c->N);
@@ -1148,7 +1150,10 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int6
   CK(c->b_med_nz.reserve(std::max<int64_t>(N, 1) * sizeof(double)));
   CK(c->b_colmin.reserve(std::max<int64_t>(N, 1) * sizeof(double)));
   CK(cudaEventRecord(c->ev[2], c->stream));
-  CK(launch_colstats(dx, S, S, N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(), c->b_colmin.as<double>(), c->stream));
+  CK(c->b_fail.reserve(sizeof(int)));
+  CK(c->b_list.reserve(std::max<int64_t>(N, 1) * sizeof(int64_t)));
+  CK(launch_colstats(dx, S, S, N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(), c->b_colmin.as<double>(),
+                     c->b_fail.as<int>(), c->b_list.as<int64_t>(), c->stream));
   c->launches += 1;
   CK(cudaEventRecord(c->ev[3], c->stream));
   c->h_med_all.resize((size_t)N);

@@ -104,8 +104,9 @@ cudaError_t launch_colabs(const int32_t* xp, const double* xx, int32_t P, int64_
 //   med_all[j]: median over non-NaN values (NaN when none)
 //   med_nz[j] : median over non-NaN, non-zero values (0 when none)        (R/plaid.R:561-566)
 //   colmin[j] : min over non-NaN values (+inf when none)
+// d_fail: 1 int, d_list: N int64 of device scratch (columns the single-pass kernel hands to the exact one)
 cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
-                            double* med_nz, double* colmin, cudaStream_t st);
+                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, cudaStream_t st);
 // out[s,j] = alpha * (x[s,j] - med[j] + c) + (beta ? beta[s] : 0); med may be nullptr (then 0)
 cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, int64_t j0, int64_t j1,
                          const double* med, double c, double alpha, const double* beta,

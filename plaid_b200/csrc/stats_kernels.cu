@@ -721,7 +721,7 @@ __global__ void k_minmax_fin(const unsigned long long* res, double* out) {
 }  // namespace
 
 cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
-                            double* med_nz, double* colmin, cudaStream_t st) {
+                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
@@ -742,13 +742,8 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
     return cudaGetLastError();
   }
   // single-pass kernel, then the exact three-pass kernel on whatever it rejected
-  int* d_fail = nullptr;
-  int64_t* d_list = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_fail, sizeof(int), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMallocAsync(&d_list, (size_t)N * sizeof(int64_t), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
+  // d_fail (1 int) and d_list (N int64) are caller-owned scratch: no allocation on the hot path
+  cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast, NT, sizeof(Stats2Smem));
@@ -770,8 +765,6 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  cudaFreeAsync(d_fail, st);
-  cudaFreeAsync(d_list, st);
   return cudaSuccess;
 }
 
