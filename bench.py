@@ -198,7 +198,7 @@ def run_ours(a):
         tnote = tj.get("note")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_score", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "score product = k_gather + k_scatter launch pair (CUDA events around both)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": tnote, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 3),
                 "kernel_share_of_step": round(score_ms / (dt / a.steps * 1e3), 3),
