@@ -102,6 +102,9 @@ class Context:
     # -- gene sets -------------------------------------------------------------------------
     def set_genesets(self, G):
         """Register matG (genes x sets, scipy sparse).  Values only matter as zero / non-zero."""
+        if G is getattr(self, "_glast", None):  # same object as last time: nothing to do (the caller must
+            return                               # not mutate a registered matrix in place)
+        self._glast = G
         G = sp.csc_matrix(G)
         G.sort_indices()
         key = (G.shape, G.nnz, hash(G.indptr.tobytes()), hash(G.indices.tobytes()), hash(G.data.tobytes()))

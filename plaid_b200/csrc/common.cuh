@@ -77,6 +77,7 @@ struct GatherParams {
   int32_t mode;
   double a0, a1;
   int32_t accumulate, final;
+  int32_t nsplit;        // CTAs per column batch (set range split), set by launch_gather
   double* out;
   int64_t ld;
 };

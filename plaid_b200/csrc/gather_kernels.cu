@@ -16,6 +16,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace plaidgpu {
 
 namespace {
@@ -33,8 +35,12 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
   double* __restrict__ stw = st + (size_t)w * GC * GPAD;
   const int K = p.K;
   const int64_t nbatch = (p.N + GC - 1) / GC;
+  // few columns (bulk data): several CTAs share one batch and split the set range between them
+  const int nsplit = p.nsplit, split = blockIdx.x % nsplit;
+  const int sgroups = (p.S + GS - 1) / GS;                       // groups of GS sets
+  const int g_lo = (int)(((int64_t)sgroups * split) / nsplit), g_hi = (int)(((int64_t)sgroups * (split + 1)) / nsplit);
 
-  for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+  for (int64_t bt = blockIdx.x / nsplit; bt < nbatch; bt += gridDim.x / nsplit) {
     const int64_t j0 = bt * GC;
     const int nc = (int)min((int64_t)GC, p.N - j0);
     // ---- stage the block's rows of X for these columns ---------------------------------
@@ -73,7 +79,7 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
     const char* __restrict__ xlane = reinterpret_cast<const char*>(Xs) + lane * 8;
     const uint4* __restrict__ ids = reinterpret_cast<const uint4*>(p.didx);
     const uint4 zrow = make_uint4((unsigned)K * 256u, (unsigned)K * 256u, (unsigned)K * 256u, (unsigned)K * 256u);
-    for (int s0 = w * GS; s0 < p.S; s0 += GW * GS) {
+    for (int s0 = (g_lo + w) * GS; s0 < g_hi * GS && s0 < p.S; s0 += GW * GS) {
       const int ns = min(GS, p.S - s0);
       const uint32_t bnd = (lane <= ns) ? (p.dptr[s0 + lane] >> 2) : 0u;  // chunk index where set lane starts
       const uint32_t cbeg = __shfl_sync(FULL, bnd, 0), cend = __shfl_sync(FULL, bnd, ns);
@@ -176,8 +182,13 @@ cudaError_t launch_gather(const GatherParams& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sms * per_sm;
   const int64_t nbatch = (p.N + GC - 1) / GC;
-  if (grid > nbatch) grid = nbatch;
-  k_gather<<<(unsigned)grid, GW * 32, smem, st>>>(p);
+  GatherParams q = p;
+  q.nsplit = 1;
+  if (nbatch < grid) {
+    q.nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(grid / nbatch, 16));
+    grid = nbatch * q.nsplit;
+  }
+  k_gather<<<(unsigned)grid, GW * 32, smem, st>>>(q);
   return cudaGetLastError();
 }
 
