@@ -81,7 +81,7 @@ struct plaidgpu_ctx {
   const int32_t* xp = nullptr;
   const int32_t* xi = nullptr;
   const double* xx = nullptr;
-  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb, b_fail, b_list;
+  DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb, b_fail, b_list, b_ci, b_cx, b_ce;
   double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
   bool need_norm = false;
   std::vector<double> h_med_all, h_med_nz, h_colmin;
@@ -483,7 +483,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
                     &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
-                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list};
+                    &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list, &c->b_ci, &c->b_cx, &c->b_ce};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -788,6 +788,18 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     p.accumulate = 1;
   }
   if (!c->dense) {
+    if (c->gblocks == 1 && c->nnz > 0) {
+      // the scatter pass never needs the gather block's entries: compact the columns once
+      CK(c->b_ci.reserve((size_t)c->nnz * sizeof(int32_t)));
+      CK(c->b_cx.reserve((size_t)c->nnz * sizeof(double)));
+      CK(c->b_ce.reserve((size_t)std::max<int64_t>(c->N, 1) * sizeof(int32_t)));
+      CK(launch_compact(c->xp, c->xi, p.xx, c->d_dmap.as<uint16_t>(), c->N, c->b_ci.as<int32_t>(), c->b_cx.as<double>(),
+                        c->b_ce.as<int32_t>(), c->stream));
+      c->launches += 1;
+      p.xi = c->b_ci.as<int32_t>();
+      p.xx = c->b_cx.as<double>();
+      p.xe = c->b_ce.as<int32_t>();
+    }
     CK(launch_score(p, false, c->cfg, c->stream));
     c->launches += 1;
   }

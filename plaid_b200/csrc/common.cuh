@@ -28,6 +28,7 @@ enum XformMode : int {
 struct ScoreParams {
   // X shard (device): CSC (xp/xi/xx) or dense column-major (xx only)
   const int32_t* xp;
+  const int32_t* xe;   // optional: end of column j (compacted columns), nullptr -> xp[j + 1]
   const int32_t* xi;
   const double* xx;   // values; for rank scorers the per-entry rank array instead
   const double* r0;   // rank scorers: rank of the zero group per column [N] (else nullptr)
@@ -92,6 +93,8 @@ struct LaunchCfg {
 cudaError_t score_configure(int device, int32_t S, int32_t tile_sets_hint, int32_t* Ts, int32_t* T,
                             LaunchCfg* cfg);
 cudaError_t launch_score(const ScoreParams& p, bool dense, const LaunchCfg& cfg, cudaStream_t st);
+cudaError_t launch_compact(const int32_t* xp, const int32_t* xi, const double* xx, const uint16_t* dmap, int64_t N,
+                           int32_t* oi, double* ox, int32_t* xe, cudaStream_t st);
 
 // gather_kernels.cu
 int gather_max_block(int device);  // largest K (genes per block) the shared-memory tile allows

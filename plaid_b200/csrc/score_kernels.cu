@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
     const int64_t k = q / T;
     const int t = (int)(q - k * T);
     const int64_t j = blockIdx.x + k * (int64_t)gridDim.x;
-    const int64_t c0 = p.xp[j], c1 = p.xp[j + 1];
+    const int64_t c0 = p.xp[j], c1 = p.xe ? p.xe[j] : p.xp[j + 1];
     double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
     if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
     // ---- batch pipeline (lane i prepares entry i of a batch) ---------------------------------
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
         unsigned char* __restrict__ tg = tag + (off >> 3);
         volatile double* a = reinterpret_cast<volatile double*>(accb + off);
         if (pend) *tg = (unsigned char)lane;
-        // (same warp, program order: every lane's tag store is performed before any lane's tag load)
+        __syncwarp();  // every lane's tag store is performed before any lane's tag load
         const unsigned tv = *reinterpret_cast<volatile unsigned char*>(tg);
         const double v0 = *a;
         const bool win = pend && tv == (unsigned)lane;
@@ -219,6 +219,51 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
     }
     __syncwarp();
   }
+}
+
+// Drop the entries of the gather block from every column once (they are a third of a single-cell column
+// and would otherwise be fetched and discarded by each of the T tile walks).  Compacted entries keep
+// their column's start offset; xe[j] = new end of column j.
+__global__ void __launch_bounds__(256) k_compact(const int32_t* __restrict__ xp, const int32_t* __restrict__ xi,
+                                                 const double* __restrict__ xx, const uint16_t* __restrict__ dmap,
+                                                 int64_t N, int32_t* __restrict__ oi, double* __restrict__ ox,
+                                                 int32_t* __restrict__ xe) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t j = w0; j < N; j += nw) {
+    const int32_t c0 = xp[j], c1 = xp[j + 1];
+    int32_t o = c0;
+    for (int32_t b = c0; b < c1; b += 32) {
+      const int32_t e = b + lane;
+      int32_t r = 0;
+      double v = 0.0;
+      bool keep = false;
+      if (e < c1) {
+        r = xi[e];
+        v = xx[e];
+        keep = dmap[r] == 0xFFFFu;
+      }
+      const unsigned m = __ballot_sync(FULL, keep);
+      if (keep) {
+        const int32_t q = o + __popc(m & lt);
+        oi[q] = r;
+        ox[q] = v;
+      }
+      o += __popc(m);
+    }
+    if (lane == 0) xe[j] = o;
+  }
+}
+
+cudaError_t launch_compact(const int32_t* xp, const int32_t* xi, const double* xx, const uint16_t* dmap, int64_t N,
+                           int32_t* oi, double* ox, int32_t* xe, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t grid = (N + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_compact<<<(unsigned)grid, 256, 0, st>>>(xp, xi, xx, dmap, N, oi, ox, xe);
+  return cudaGetLastError();
 }
 
 cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* Ts_out, int32_t* T_out,
