@@ -258,6 +258,39 @@ def test_chunked_crossprod_matches(gpu_ctx):
     assert rel_err(pb.chunked_crossprod(G, X, chunk=7, ctx=gpu_ctx), O.chunked_crossprod(G, X, chunk=7)) < TOL
 
 
+def test_degenerate_shapes(gpu_ctx):
+    """N = 1, S = 1, empty matrix, empty columns, a set of ALL genes, S above 2^16 (reference benchmark: 61k sets)"""
+    P = 400
+    names = synth.gene_names(P)
+    X = synth.sparse_x_numpy(P, 9, seed=101, density=0.2).tolil()
+    X[:, 2] = 0
+    X[:, 8] = 0
+    X = sp.csc_matrix(X)
+    G1 = sp.csc_matrix(np.ones((P, 1)))                        # one set holding every gene
+    for G in (G1, synth.genesets_numpy(P, 3, seed=102, size_cap=(3, 50))):
+        for norm in (False, True):
+            got = pb.plaid(pb.NamedMatrix(X, names), pb.NamedMatrix(G, names), normalize=norm, ctx=gpu_ctx).mat
+            assert rel_err(got, O.plaid(O.Named(X, names), O.Named(G, names), normalize=norm).mat) < TOL
+    one = pb.plaid(pb.NamedMatrix(X[:, :1], names), pb.NamedMatrix(G1, names), ctx=gpu_ctx).mat
+    assert one.shape == (1, 1)
+    Z = sp.csc_matrix((P, 5))                                   # nothing stored at all
+    Gz = synth.genesets_numpy(P, 40, seed=103, size_cap=(3, 50))
+    got = pb.plaid(pb.NamedMatrix(Z, names), pb.NamedMatrix(Gz, names), ctx=gpu_ctx).mat
+    assert rel_err(got, O.plaid(O.Named(Z, names), O.Named(Gz, names)).mat) < TOL
+    assert np.array_equal(pb.colranks(Z, ctx=gpu_ctx), O.colranks(Z))
+    assert rel_err(pb.replaid_ucell(pb.NamedMatrix(X, names), pb.NamedMatrix(Gz, names), ctx=gpu_ctx).mat,
+                   O.replaid_ucell(O.Named(X, names), O.Named(Gz, names)).mat) < TOL
+    # more sets than fit 16 bits (the reference benchmarks 61,459 sets): tiles + gather block + 32-bit offsets
+    P2, N2, S2 = 3000, 40, 70001
+    X2 = synth.sparse_x_numpy(P2, N2, seed=104)
+    G2 = synth.genesets_numpy(P2, 2000, seed=105, size_cap=(5, 100))
+    G2 = sp.hstack([G2] * 36).tocsc()[:, :S2]
+    n2 = synth.gene_names(P2)
+    got = pb.plaid(pb.NamedMatrix(X2, n2), pb.NamedMatrix(G2, n2), ctx=gpu_ctx).mat
+    assert got.shape == (S2, N2)
+    assert rel_err(got, O.plaid(O.Named(X2, n2), O.Named(G2, n2)).mat) < TOL
+
+
 def test_sharded_protocol_is_shard_count_invariant():
     """column shards on separate contexts (begin / compute / finish with exchanged scalars) give exactly
     the single-context result, for 2 and 3 ragged shards (multi-GPU invariance)"""
