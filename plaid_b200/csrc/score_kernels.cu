@@ -274,7 +274,7 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
   int warps = 16;
   if (const char* w = getenv("PLAIDGPU_WARPS")) {  // tuning knob (bench / profiling only)
     const int v = atoi(w);
-    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) warps = v;
+    if (v >= 1 && v <= 16) warps = v;
   }
   const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin - 1024;  // leave the 1 KB reserve
   // per warp: Ts fp64 accumulators + Ts byte tags (16-byte aligned) + 32 staged gene records of 32 B
