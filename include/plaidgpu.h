@@ -201,6 +201,16 @@ int plaidgpu_colranks(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, int ties, int
 int plaidgpu_normalize_medians(plaidgpu_ctx* ctx, const double* x, int32_t S, int64_t N,
                                int ignore_zero, int location, double* out);
 
+/* ---- differential enrichment on the scores ("next" row f1 of the scope table) ------------- */
+
+/* Per gene set (row of the S x N score matrix) the sums and sums of squares over the samples of each
+ * group y[j] in {0, 1}: the reductions behind plaid.test(tests = "lm") (Rfast::ttests on t(gsetX),
+ * reference R/plaid.R:429-431).  x: S x N column-major doubles at `location`; y: host int32[N];
+ * out: host double[4 * S] = {sum0[S], sumsq0[S], sum1[S], sumsq1[S]}.  Columns are added in a fixed
+ * order, so results are bit-reproducible.  The t statistics / p-values stay on the host (stats::pt). */
+int plaidgpu_group_moments(plaidgpu_ctx* ctx, const double* x, int32_t S, int64_t N, const int32_t* y,
+                           int location, double* out);
+
 /* ---- introspection (bench / tests) ------------------------------------------------ */
 
 /* number of kernels launched by this context since creation (or since reset) */

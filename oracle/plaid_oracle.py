@@ -372,3 +372,135 @@ def replaid_gsva(X: Named, matG: Named, tau: float = 0.0, rowtf: str = "z"):
     if tau > 0:
         rX = np.sign(rX) * np.abs(rX) ** (1 + tau)  # :356
     return plaid(Named(rX, X.rownames, X.colnames), matG)
+
+
+# ----------------------------------------------------------------------------------
+# plaid.test  ("next" row f1 of the scope table; the statistics downstream of the scores)
+# ----------------------------------------------------------------------------------
+def _pt_upper2(t, df):
+    """2 * pt(|t|, df, lower.tail = FALSE)"""
+    from scipy import stats
+    return 2.0 * stats.t.sf(np.abs(t), df)
+
+
+def matrix_onesample_ttest(F: np.ndarray, G) -> dict:
+    """`matrix_onesample_ttest` (R/plaid.R:476-486); F: genes x k, G: genes x sets."""
+    Gb = (_as_csc(G) != 0).astype(np.float64)
+    F = np.asarray(F, dtype=np.float64).reshape(Gb.shape[0], -1)
+    sumG = np.asarray(Gb.sum(axis=0)).ravel()
+    sum_sq = np.asarray(Gb.T @ (F ** 2))
+    meanx = np.asarray(Gb.T @ F) / (1e-8 + sumG)[:, None]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sdx = np.sqrt((sum_sq - meanx ** 2 * sumG[:, None]) / (sumG - 1)[:, None])
+        t = meanx / (1e-8 + sdx) * np.sqrt(sumG)[:, None]
+    p = _pt_upper2(t, np.maximum(sumG - 1, 1)[:, None])
+    return {"mean": meanx, "t": t, "p": p}
+
+
+def matrix_twosample_ttest(F: np.ndarray, G) -> dict:
+    """`matrix_twosample_ttest` (R/plaid.R:488-520)."""
+    Gb = (_as_csc(G) != 0).astype(np.float64)
+    F = np.asarray(F, dtype=np.float64).reshape(Gb.shape[0], -1)
+    sum1 = np.asarray(Gb.sum(axis=0)).ravel()[:, None]
+    sum0 = Gb.shape[0] - sum1
+    F2 = F ** 2
+    ssq1 = np.asarray(Gb.T @ F2)
+    ssq0 = -ssq1 + F2.sum(axis=0)[None, :]
+    mean1 = np.asarray(Gb.T @ F)
+    mean0 = -mean1 + F.sum(axis=0)[None, :]
+    mean1 = mean1 / (1e-8 + sum1)
+    mean0 = mean0 / (1e-8 + sum0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        var0 = (ssq0 - mean0 ** 2 * sum0) / (sum0 - 1)
+        var1 = (ssq1 - mean1 ** 2 * sum1) / (sum1 - 1)
+        varsum = var0 / sum0 + var1 / sum1
+        dof = varsum ** 2 / (var0 / sum0 * (sum0 - 1) + var1 / sum1 * (sum1 - 1))  # exactly as written at :510
+        f = mean1 - mean0
+        t = f / np.sqrt(varsum)
+    p = _pt_upper2(t, np.maximum(dof, 1))
+    return {"diff": f, "t": t, "p": p}
+
+
+def ttests_welch(M: np.ndarray, y: np.ndarray) -> dict:
+    """Rfast::ttests(t(M), ina = y + 1) (R/plaid.R:429): per row of M a Welch two-sample t-test between the
+    columns with y == 0 (ina 1) and y == 1 (ina 2)."""
+    M = np.asarray(M, dtype=np.float64)
+    a, b = M[:, y == 0], M[:, y == 1]
+    n1, n2 = a.shape[1], b.shape[1]
+    m1, m2 = a.mean(axis=1), b.mean(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        v1 = ((a ** 2).sum(axis=1) - n1 * m1 ** 2) / (n1 - 1)
+        v2 = ((b ** 2).sum(axis=1) - n2 * m2 ** 2) / (n2 - 1)
+        fac = v1 / n1 + v2 / n2
+        stat = (m1 - m2) / np.sqrt(fac)
+        dof = fac ** 2 / ((v1 / n1) ** 2 / (n1 - 1) + (v2 / n2) ** 2 / (n2 - 1))
+    return {"stat": stat, "pvalue": _pt_upper2(stat, dof), "dof": dof}
+
+
+def p_adjust_fdr(p: np.ndarray) -> np.ndarray:
+    """stats::p.adjust(p, method = "fdr") (Benjamini-Hochberg)."""
+    p = np.asarray(p, dtype=np.float64)
+    n = p.size
+    o = np.argsort(-p, kind="stable")
+    ro = np.argsort(o, kind="stable")
+    q = np.minimum.accumulate(p[o] * n / np.arange(n, 0, -1))
+    return np.minimum(q, 1.0)[ro]
+
+
+def plaid_test(X: Named, y, G: Named, gsetX: Optional[Named] = None, tests=("one", "two", "lm"),
+               metap_method: str = "fisher", sort_by: str = "p.meta"):
+    """`plaid.test` (R/plaid.R:392-474).  Returns (table ndarray, column names, row names) sorted by `sort_by`."""
+    from scipy import stats
+    y = np.asarray(y)
+    if not np.all(np.isin(np.unique(y), [0, 1])):
+        raise ValueError("elements of y must be 0 or 1")
+    gg = [g for g in dict.fromkeys(G.rownames) if g in set(X.rownames)]  # intersect(rownames(G), rownames(X)), :402
+    xpos = {}
+    for k, n in enumerate(X.rownames):
+        xpos.setdefault(n, k)
+    gpos = {}
+    for k, n in enumerate(G.rownames):
+        gpos.setdefault(n, k)
+    xi = np.array([xpos[g] for g in gg])
+    gi = np.array([gpos[g] for g in gg])
+    Xm = X.mat.tocsr()[xi].toarray() if _is_sparse(X.mat) else np.asarray(X.mat, dtype=np.float64)[xi]
+    Gm = _as_csc(G.mat).tocsr()[gi].tocsc()
+    fc = Xm[:, y == 1].mean(axis=1) - Xm[:, y == 0].mean(axis=1)  # :406-408
+    P, Fs = {}, {}
+    if "one" in tests:
+        r = matrix_onesample_ttest(fc, Gm)
+        P["one"], Fs["one"] = r["p"][:, 0], r["mean"][:, 0]
+    if "two" in tests:
+        r = matrix_twosample_ttest(fc, Gm)
+        P["two"], Fs["two"] = r["p"][:, 0], r["diff"][:, 0]
+    if "lm" in tests:
+        if gsetX is None:
+            gsetX = plaid(Named(Xm, gg, X.colnames), Named(Gm, gg, G.colnames))
+        r = ttests_welch(gsetX.mat, y)
+        P["lm"] = r["pvalue"]
+        Fs["lm"] = gsetX.mat[:, y == 1].mean(axis=1) - gsetX.mat[:, y == 0].mean(axis=1)
+    for k in P:  # :440-445
+        p1 = np.where(np.isnan(P[k]), 1.0, P[k])
+        P[k] = np.minimum(np.maximum(p1, 1e-99), 1 - 1e-99)
+    keys = [k for k in ("one", "two", "lm") if k in P]
+    Fm = np.column_stack([Fs[k] for k in keys])
+    gsetFC = Fm.mean(axis=1)
+    if len(keys) > 1:  # matrix_combine_p (:522-537)
+        if metap_method in ("fisher", "sumlog"):
+            chisq = -2.0 * sum(np.log(P[k]) for k in keys)
+            pmeta = stats.chi2.sf(chisq, 2 * len(keys))
+        elif metap_method in ("stouffer", "sumz"):
+            zz = sum(stats.norm.isf(P[k]) for k in keys) / math.sqrt(len(keys))
+            pmeta = stats.norm.sf(zz)
+        else:
+            raise ValueError("Invalid method: " + metap_method)
+    else:
+        pmeta = P[keys[0]]
+    qmeta = p_adjust_fdr(pmeta)
+    cols = ["gsetFC"] + ["p." + k for k in keys] + ["p.meta", "q.meta"]
+    tab = np.column_stack([gsetFC] + [P[k] for k in keys] + [pmeta, qmeta])
+    rows = list(G.colnames) if G.colnames is not None else [str(k) for k in range(tab.shape[0])]
+    if sort_by in cols:
+        o = np.argsort(tab[:, cols.index(sort_by)], kind="stable")
+        tab, rows = tab[o], [rows[k] for k in o]
+    return tab, cols, rows

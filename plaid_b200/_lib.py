@@ -57,6 +57,7 @@ SYMBOLS = {
     "plaidgpu_crossprod": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "plaidgpu_row_moments": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.c_void_p]),
     "plaidgpu_colranks": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "plaidgpu_group_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "plaidgpu_normalize_medians": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "plaidgpu_launch_count": (C.c_int64, [C.c_void_p]),
     "plaidgpu_reset_launch_count": (None, [C.c_void_p]),

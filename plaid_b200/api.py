@@ -403,3 +403,109 @@ def replaid_gsva(X: NamedMatrix, matG: NamedMatrix, tau: float = 0.0, rowtf: str
     if rowtf != "z":
         raise ValueError("Error: unknown row transform" + str(rowtf))  # R/plaid.R:348
     return _score(X, matG, dict(scorer=L.GSVA, tau=float(tau)), ctx, out)
+
+
+# ---------------------------------------------------------------------------------------
+# plaid.test: the reductions run on the GPU, the distribution functions stay on the host (as stats::pt does in R)
+# ---------------------------------------------------------------------------------------
+def group_moments(gsetX, y, *, ctx=None):
+    """Per row of a dense S x N matrix: (sum, sum of squares) over the columns with y == 0 and with y == 1
+    (`plaidgpu_group_moments`); the reductions of Rfast::ttests in plaid.test (R/plaid.R:429-431)."""
+    ctx = ctx or default_context()
+    y32 = np.ascontiguousarray(np.asarray(y), dtype=np.int32)
+    if _is_torch(gsetX):
+        raise TypeError("pass device matrices through the C ABI directly")
+    a = np.asfortranarray(np.asarray(gsetX, dtype=np.float64))
+    out = np.empty((4, a.shape[0]), dtype=np.float64)
+    ctx.check(ctx.lib.plaidgpu_group_moments(ctx.h, a.ctypes.data, a.shape[0], a.shape[1], y32.ctypes.data, L.HOST,
+                                             out.ctypes.data))
+    return out
+
+
+def plaid_test(X: NamedMatrix, y, G: NamedMatrix, gsetX: Optional[NamedMatrix] = None, tests=("one", "two", "lm"),
+               metap_method: str = "fisher", sort_by: str = "p.meta", *, ctx=None):
+    """`plaid.test(X, y, G, gsetX, tests=c("one","two","lm"), metap.method="fisher", sort.by="p.meta")`
+    (R/plaid.R:392-474).  GPU: the score matrix (plaid), the crossprods of the one/two-sample tests
+    (chunked_crossprod on G != 0) and the per-set group moments of the "lm" test; host: pt / pchisq / p.adjust.
+    Returns (table, column names, row names) like the oracle."""
+    from scipy import stats
+    ctx = ctx or default_context()
+    y = np.asarray(y)
+    if not np.all(np.isin(np.unique(y), [0, 1])):
+        raise ValueError("elements of y must be 0 or 1")  # R/plaid.R:394
+    xset = set(X.rownames)
+    gg = [g for g in dict.fromkeys(G.rownames) if g in xset]
+    xpos, gpos = {}, {}
+    for k, n in enumerate(X.rownames):
+        xpos.setdefault(n, k)
+    for k, n in enumerate(G.rownames):
+        gpos.setdefault(n, k)
+    xi = np.array([xpos[g] for g in gg])
+    gi = np.array([gpos[g] for g in gg])
+    Xs = sp.csc_matrix(X.mat).tocsr()[xi].tocsc() if sp.issparse(X.mat) else np.asarray(X.mat, dtype=np.float64)[xi]
+    Gs = sp.csc_matrix(G.mat).tocsr()[gi].tocsc()
+    n1, n0 = int((y == 1).sum()), int((y == 0).sum())
+    if sp.issparse(Xs):
+        fc = np.asarray(Xs[:, y == 1].sum(axis=1)).ravel() / n1 - np.asarray(Xs[:, y == 0].sum(axis=1)).ravel() / n0
+    else:
+        fc = Xs[:, y == 1].mean(axis=1) - Xs[:, y == 0].mean(axis=1)
+    Gb = Gs.copy()
+    Gb.data = (Gb.data != 0).astype(np.float64)
+    Gb.eliminate_zeros()
+    sumG = np.asarray(Gb.sum(axis=0)).ravel()
+    P, Fs = {}, {}
+    if "one" in tests or "two" in tests:
+        cp = chunked_crossprod(Gb, np.column_stack([fc, fc ** 2]), ctx=ctx)  # crossprod(G != 0, [F, F^2]) on the GPU
+        s1, q1 = cp[:, 0], cp[:, 1]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if "one" in tests:  # R/plaid.R:476-486
+            meanx = s1 / (1e-8 + sumG)
+            sdx = np.sqrt((q1 - meanx ** 2 * sumG) / (sumG - 1))
+            t = meanx / (1e-8 + sdx) * np.sqrt(sumG)
+            P["one"], Fs["one"] = 2.0 * stats.t.sf(np.abs(t), np.maximum(sumG - 1, 1)), meanx
+        if "two" in tests:  # R/plaid.R:488-520
+            sum1, sum0 = sumG, Gb.shape[0] - sumG
+            ssq0, m0 = -q1 + (fc ** 2).sum(), -s1 + fc.sum()
+            mean1, mean0 = s1 / (1e-8 + sum1), m0 / (1e-8 + sum0)
+            var0 = (ssq0 - mean0 ** 2 * sum0) / (sum0 - 1)
+            var1 = (q1 - mean1 ** 2 * sum1) / (sum1 - 1)
+            varsum = var0 / sum0 + var1 / sum1
+            dof = varsum ** 2 / (var0 / sum0 * (sum0 - 1) + var1 / sum1 * (sum1 - 1))
+            f = mean1 - mean0
+            P["two"], Fs["two"] = 2.0 * stats.t.sf(np.abs(f / np.sqrt(varsum)), np.maximum(dof, 1)), f
+        if "lm" in tests:  # R/plaid.R:423-433
+            if gsetX is None:
+                _message("[plaid.test] computing plaid scores...")
+                gsetX = plaid(NamedMatrix(Xs, gg, X.colnames), NamedMatrix(Gs, gg, G.colnames), ctx=ctx)
+            gm = group_moments(gsetX.mat, y, ctx=ctx)
+            m1, m2 = gm[0] / n0, gm[2] / n1  # ina 1 = (y == 0), ina 2 = (y == 1)
+            v1 = (gm[1] - n0 * m1 ** 2) / (n0 - 1)
+            v2 = (gm[3] - n1 * m2 ** 2) / (n1 - 1)
+            fac = v1 / n0 + v2 / n1
+            stat = (m1 - m2) / np.sqrt(fac)
+            dof = fac ** 2 / ((v1 / n0) ** 2 / (n0 - 1) + (v2 / n1) ** 2 / (n1 - 1))
+            P["lm"], Fs["lm"] = 2.0 * stats.t.sf(np.abs(stat), dof), m2 - m1
+    for k in P:
+        p1 = np.where(np.isnan(P[k]), 1.0, P[k])
+        P[k] = np.minimum(np.maximum(p1, 1e-99), 1 - 1e-99)
+    keys = [k for k in ("one", "two", "lm") if k in P]
+    gsetFC = np.column_stack([Fs[k] for k in keys]).mean(axis=1)
+    if len(keys) > 1:
+        if metap_method in ("fisher", "sumlog"):
+            pmeta = stats.chi2.sf(-2.0 * sum(np.log(P[k]) for k in keys), 2 * len(keys))
+        elif metap_method in ("stouffer", "sumz"):
+            pmeta = stats.norm.sf(sum(stats.norm.isf(P[k]) for k in keys) / math.sqrt(len(keys)))
+        else:
+            raise ValueError("Invalid method: " + metap_method)
+    else:
+        pmeta = P[keys[0]]
+    n = pmeta.size  # p.adjust(method = "fdr")
+    o = np.argsort(-pmeta, kind="stable")
+    q = np.minimum(np.minimum.accumulate(pmeta[o] * n / np.arange(n, 0, -1)), 1.0)[np.argsort(o, kind="stable")]
+    cols = ["gsetFC"] + ["p." + k for k in keys] + ["p.meta", "q.meta"]
+    tab = np.column_stack([gsetFC] + [P[k] for k in keys] + [pmeta, q])
+    rows = list(G.colnames) if G.colnames is not None else [str(k) for k in range(tab.shape[0])]
+    if sort_by in cols:
+        oo = np.argsort(tab[:, cols.index(sort_by)], kind="stable")
+        tab, rows = tab[oo], [rows[k] for k in oo]
+    return tab, cols, rows

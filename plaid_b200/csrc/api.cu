@@ -1143,6 +1143,31 @@ int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int i
   return PLAIDGPU_OK;
 }
 
+int plaidgpu_group_moments(plaidgpu_ctx* c, const double* x, int32_t S, int64_t N, const int32_t* y, int location,
+                           double* out) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (S <= 0 || N < 0 || !out || (N > 0 && (!x || !y))) return fail(c, PLAIDGPU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  const int64_t total = (int64_t)S * N;
+  const double* dx = x;
+  if (location == PLAIDGPU_HOST) {
+    CK(c->b_raw.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+    if (total) CK(cudaMemcpyAsync(c->b_raw.p, x, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dx = c->b_raw.as<double>();
+  }
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
+  CK(c->b_i32.reserve((size_t)std::max<int64_t>(N, 1) * sizeof(int32_t)));
+  if (N) CK(cudaMemcpyAsync(c->b_i32.p, y, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(c->b_rowa.reserve((size_t)nchunk * 4 * S * sizeof(double)));
+  CK(c->b_rowb.reserve((size_t)4 * S * sizeof(double)));
+  CK(launch_group_moments(dx, S, S, N, c->b_i32.as<int32_t>(), nchunk, c->b_rowa.as<double>(), c->b_rowb.as<double>(),
+                          c->stream));
+  c->launches += 2;
+  CK(cudaMemcpyAsync(out, c->b_rowb.p, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PLAIDGPU_OK;
+}
+
 // -----------------------------------------------------------------------------------------
 int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int64_t N, int ignore_zero,
                                int location, double* out) {

@@ -115,6 +115,10 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
 cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, int64_t j0, int64_t j1,
                          const double* med, double c, double alpha, const double* beta,
                          cudaStream_t st);
+// per-row sums / sums of squares by column group (plaid.test "lm"): partial = nchunk * 4 * S doubles of scratch,
+// out = 4 * S doubles {sum0, sumsq0, sum1, sumsq1}; fixed summation order
+cudaError_t launch_group_moments(const double* x, int64_t ld, int32_t S, int64_t N, const int32_t* y, int nchunk,
+                                 double* partial, double* out, cudaStream_t st);
 // global min / max of a device array of n doubles, NaN ignored (na.rm = TRUE); res[0]=min res[1]=max
 cudaError_t launch_minmax(const double* x, int64_t n, double* res2, cudaStream_t st);
 

@@ -709,6 +709,42 @@ __global__ void __launch_bounds__(256) k_minmax(const double* __restrict__ x, in
   }
 }
 
+// row sums / sums of squares of a column-major S x N matrix by column group y[j] in {0,1}.
+// grid = (row blocks, column chunks); partial[chunk][4][S] are combined in chunk order by k_group_combine.
+__global__ void __launch_bounds__(256) k_group_partial(const double* __restrict__ x, int64_t ld, int32_t S, int64_t N,
+                                                       const int32_t* __restrict__ y, int nchunk,
+                                                       double* __restrict__ partial) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.y;
+  const int64_t j0 = (N * ch) / nchunk, j1 = (N * (ch + 1)) / nchunk;
+  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+  if (r < S) {
+    for (int64_t j = j0; j < j1; ++j) {
+      const double v = __ldcs(x + j * ld + r);
+      if (y[j]) {
+        s1 += v;
+        q1 += v * v;
+      } else {
+        s0 += v;
+        q0 += v * v;
+      }
+    }
+    double* p = partial + (size_t)ch * 4 * S;
+    p[r] = s0;
+    p[S + r] = q0;
+    p[2 * (size_t)S + r] = s1;
+    p[3 * (size_t)S + r] = q1;
+  }
+}
+__global__ void __launch_bounds__(256) k_group_combine(const double* __restrict__ partial, int32_t S, int nchunk,
+                                                       double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= 4 * (int64_t)S) return;
+  double a = 0.0;
+  for (int ch = 0; ch < nchunk; ++ch) a += partial[(size_t)ch * 4 * S + i];
+  out[i] = a;
+}
+
 __global__ void k_minmax_init(unsigned long long* res) {
   res[0] = ~0ull;
   res[1] = 0ull;
@@ -778,6 +814,17 @@ cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, in
   int64_t grid = (int64_t)sms * 8;
   if (grid > j1 - j0) grid = j1 - j0;
   k_fixup<<<(unsigned)grid, 256, 0, st>>>(x, out, ld, S, j0, j1, med, c, alpha, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_group_moments(const double* x, int64_t ld, int32_t S, int64_t N, const int32_t* y, int nchunk,
+                                 double* partial, double* out, cudaStream_t st) {
+  if (S <= 0) return cudaSuccess;
+  dim3 g((unsigned)((S + 255) / 256), (unsigned)nchunk);
+  k_group_partial<<<g, 256, 0, st>>>(x, ld, S, N, y, nchunk, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_group_combine<<<(unsigned)((4 * (int64_t)S + 255) / 256), 256, 0, st>>>(partial, S, nchunk, out);
   return cudaGetLastError();
 }
 

@@ -120,3 +120,79 @@ replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1]) {      # R
   if (rowtf != "z") stop("Error: unknown row transform", rowtf)              # R/plaid.R:348
   .score(X, matG, list(scorer = 6L, tau = as.numeric(tau)))
 }
+
+## plaid.test (R/plaid.R:392-474): same arguments and result table; the score matrix, the set-wise sums of
+## logFC / logFC^2 and the per-set group moments come from the GPU, pt / pchisq / p.adjust stay in R.
+plaid.test <- function(X, y, G, gsetX, tests = c("one", "two", "lm"),
+                       metap.method = "fisher", sort.by = "p.meta") {
+  if (!all(unique(y) %in% c(0, 1))) stop("elements of y must be 0 or 1")
+  if (is.list(G)) stop("plaid.test: pass the gene sets as a sparse matrix (gmt2mat())")
+  gg <- intersect(rownames(G), rownames(X))
+  X <- X[gg, , drop = FALSE]
+  G <- G[gg, , drop = FALSE]
+  n1 <- sum(y == 1); n0 <- sum(y == 0)
+  fc <- Matrix::rowMeans(X[, y == 1, drop = FALSE]) - Matrix::rowMeans(X[, y == 0, drop = FALSE])
+  B <- 1 * (G != 0)
+  sumG <- Matrix::colSums(B)
+  pv <- list(); ff <- list()
+  if (any(c("one", "two") %in% tests)) {
+    sq <- chunked_crossprod(B, cbind(fc, fc^2))           # GPU: t(G != 0) %*% [F, F^2]
+    s1 <- sq[, 1]; q1 <- sq[, 2]
+  }
+  if ("one" %in% tests) {
+    mx <- s1 / (1e-8 + sumG)
+    sdx <- sqrt((q1 - mx^2 * sumG) / (sumG - 1))
+    tt <- mx / (1e-8 + sdx) * sqrt(sumG)
+    pv$one <- 2 * stats::pt(abs(tt), df = pmax(sumG - 1, 1), lower.tail = FALSE); ff$one <- mx
+  }
+  if ("two" %in% tests) {
+    sum0 <- nrow(B) - sumG
+    mean1 <- s1 / (1e-8 + sumG); mean0 <- (sum(fc) - s1) / (1e-8 + sum0)
+    var0 <- ((sum(fc^2) - q1) - mean0^2 * sum0) / (sum0 - 1)
+    var1 <- (q1 - mean1^2 * sumG) / (sumG - 1)
+    vs <- var0 / sum0 + var1 / sumG
+    dof <- vs^2 / (var0 / sum0 * (sum0 - 1) + var1 / sumG * (sumG - 1))
+    pv$two <- 2 * stats::pt(abs((mean1 - mean0) / sqrt(vs)), df = pmax(dof, 1), lower.tail = FALSE)
+    ff$two <- mean1 - mean0
+  }
+  if ("lm" %in% tests) {
+    if (is.null(gsetX)) {
+      message("[plaid.test] computing plaid scores...")
+      gsetX <- plaid(X, G)
+    }
+    gm <- .Call(C_plaidgpu_group_moments, .ctx(), gsetX, as.integer(y))
+    m0 <- gm[, 1] / n0; m1 <- gm[, 3] / n1
+    v0 <- (gm[, 2] - n0 * m0^2) / (n0 - 1); v1 <- (gm[, 4] - n1 * m1^2) / (n1 - 1)
+    fac <- v0 / n0 + v1 / n1
+    dof <- fac^2 / ((v0 / n0)^2 / (n0 - 1) + (v1 / n1)^2 / (n1 - 1))
+    pv$lm <- 2 * stats::pt(abs((m0 - m1) / sqrt(fac)), df = dof, lower.tail = FALSE); ff$lm <- m1 - m0
+  }
+  pv <- lapply(pv, function(p) { p[is.na(p)] <- 1; pmin(pmax(p, 1e-99), 1 - 1e-99) })
+  gsetFC <- rowMeans(do.call(cbind, ff))
+  if (length(pv) > 1) {
+    if (metap.method %in% c("fisher", "sumlog")) {
+      pmeta <- stats::pchisq(-2 * Reduce(`+`, lapply(pv, log)), 2 * length(pv), lower.tail = FALSE)
+    } else if (metap.method %in% c("stouffer", "sumz")) {
+      pmeta <- stats::pnorm(Reduce(`+`, lapply(pv, stats::qnorm, lower.tail = FALSE)) / sqrt(length(pv)), lower.tail = FALSE)
+    } else stop("Invalid method: ", metap.method)
+  } else pmeta <- pv[[1]]
+  P <- do.call(cbind, pv); colnames(P) <- paste0("p.", names(pv))
+  res <- cbind(gsetFC = gsetFC, P, p.meta = pmeta, q.meta = stats::p.adjust(pmeta, method = "fdr"))
+  rownames(res) <- colnames(G)
+  if (sort.by %in% colnames(res)) res <- res[order(res[, sort.by]), ]
+  res
+}
+
+chunked_crossprod <- function(x, y, chunk = NULL) {                         # R/plaid.R:100-123
+  x <- methods::as(x, "CsparseMatrix")
+  sc <- rep(1, ncol(x))                      # x must be column-scaled binary (what plaid() builds)
+  nz <- diff(x@p) > 0
+  sc[nz] <- x@x[x@p[-length(x@p)][nz] + 1L]
+  if (is.null(chunk) || chunk < 0) chunk <- round(0.8 * .Machine$integer.max / ncol(x))
+  if (NCOL(y) >= chunk) message("[chunked_crossprod] chunked compute: chunk = ", chunk)
+  yy <- .as_x(y)
+  out <- .Call(C_plaidgpu_crossprod, .ctx(), yy$kind, yy$p, yy$i, yy$x, as.integer(yy$dim),
+               x@p, x@i, x@x, as.integer(dim(x)), as.numeric(sc))
+  dimnames(out) <- list(colnames(x), yy$dimnames[[2]])
+  out
+}

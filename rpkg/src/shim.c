@@ -93,6 +93,28 @@ SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim,
   return out;
 }
 
+/* chunked_crossprod(x, y): t(x) %*% y for a column-scaled binary sparse x */
+SEXP C_plaidgpu_crossprod(SEXP ctx, SEXP kind, SEXP Yp, SEXP Yi, SEXP Yx, SEXP Ydim, SEXP Gp, SEXP Gi, SEXP Gx,
+                          SEXP Gdim, SEXP colscale) {
+  plaidgpu_ctx* c = get_ctx(ctx);
+  const int PG = INTEGER(Gdim)[0], S = INTEGER(Gdim)[1];
+  int rc = plaidgpu_set_genesets(c, PG, S, INTEGER(Gp), INTEGER(Gi), REAL(Gx));
+  if (rc != PLAIDGPU_OK) Rf_error("plaidgpu_set_genesets: %s", plaidgpu_last_error(c));
+  plaidgpu_matrix M;
+  fill_matrix(&M, Rf_asInteger(kind), Yp, Yi, Yx, Ydim);
+  if (M.P != PG) Rf_error("non-conformable arguments");
+  int* rowmap = (int*)R_alloc((size_t)PG, sizeof(int)); /* identity: same rows on both sides */
+  for (int r = 0; r < PG; ++r) rowmap[r] = r;
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, S, (int)M.N));
+  rc = plaidgpu_crossprod(c, &M, rowmap, REAL(colscale), PLAIDGPU_HOST, REAL(out));
+  if (rc != PLAIDGPU_OK) {
+    UNPROTECT(1);
+    Rf_error("plaidgpu_crossprod: %s", plaidgpu_last_error(c));
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 /* normalize_medians(x, ignore.zero) */
 SEXP C_plaidgpu_normalize_medians(SEXP ctx, SEXP x, SEXP ignore_zero) {
   plaidgpu_ctx* c = get_ctx(ctx);
@@ -126,11 +148,28 @@ SEXP C_plaidgpu_colranks(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xd
   return out;
 }
 
+/* per-set sums / sums of squares of gsetX by group y (plaid.test "lm"): 4 x S matrix */
+SEXP C_plaidgpu_group_moments(SEXP ctx, SEXP x, SEXP y) {
+  plaidgpu_ctx* c = get_ctx(ctx);
+  SEXP dim = Rf_getAttrib(x, R_DimSymbol);
+  const int S = INTEGER(dim)[0], N = INTEGER(dim)[1];
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, S, 4)); /* columns: sum0, sumsq0, sum1, sumsq1 */
+  int rc = plaidgpu_group_moments(c, REAL(x), S, N, INTEGER(y), PLAIDGPU_HOST, REAL(out));
+  if (rc != PLAIDGPU_OK) {
+    UNPROTECT(1);
+    Rf_error("plaidgpu_group_moments: %s", plaidgpu_last_error(c));
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_plaidgpu_ctx", (DL_FUNC)&C_plaidgpu_ctx, 1},
     {"C_plaidgpu_score", (DL_FUNC)&C_plaidgpu_score, 12},
     {"C_plaidgpu_normalize_medians", (DL_FUNC)&C_plaidgpu_normalize_medians, 3},
     {"C_plaidgpu_colranks", (DL_FUNC)&C_plaidgpu_colranks, 9},
+    {"C_plaidgpu_group_moments", (DL_FUNC)&C_plaidgpu_group_moments, 3},
+    {"C_plaidgpu_crossprod", (DL_FUNC)&C_plaidgpu_crossprod, 11},
     {NULL, NULL, 0}};
 
 void R_init_plaid(DllInfo* dll) {

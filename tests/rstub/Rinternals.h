@@ -16,3 +16,4 @@ SEXP Rf_allocMatrix(int, int, int); SEXP Rf_allocVector(int, R_xlen_t); SEXP Rf_
 void Rf_error(const char*, ...) __attribute__((noreturn));
 void* R_ExternalPtrAddr(SEXP); void R_ClearExternalPtr(SEXP); SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void R_RegisterCFinalizerEx(SEXP, void (*)(SEXP), Rboolean);
+char* R_alloc(size_t, int);

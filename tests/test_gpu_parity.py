@@ -258,6 +258,25 @@ def test_chunked_crossprod_matches(gpu_ctx):
     assert rel_err(pb.chunked_crossprod(G, X, chunk=7, ctx=gpu_ctx), O.chunked_crossprod(G, X, chunk=7)) < TOL
 
 
+def test_plaid_test_statistics(gpu_ctx):
+    """plaid.test (R/plaid.R:392-474): GPU reductions + host distribution functions vs the oracle restatement"""
+    P, N, S = 900, 60, 120
+    X = synth.sparse_x_numpy(P, N, seed=111, density=0.3)
+    G = synth.genesets_numpy(P, S, seed=112, size_cap=(5, 120))
+    names = synth.gene_names(P)
+    y = (np.random.default_rng(3).random(N) < 0.4).astype(int)
+    sets = synth.set_names(S)
+    got = pb.plaid_test(pb.NamedMatrix(X, names), y, pb.NamedMatrix(G, names, sets), ctx=gpu_ctx)
+    want = O.plaid_test(O.Named(X, names, None), y, O.Named(G, names, sets))
+    assert got[1] == want[1] and sorted(got[2]) == sorted(want[2])
+    # rows are sorted by p.meta; align by set name (near-equal p-values may swap places at the 1e-15 level)
+    go, wo = np.argsort(got[2]), np.argsort(want[2])
+    assert rel_err(got[0][go], want[0][wo]) < 1e-8
+    assert np.all(np.diff(got[0][:, got[1].index("p.meta")]) >= 0)
+    gm = pb.group_moments(np.arange(12.0).reshape(3, 4), [0, 1, 1, 0], ctx=gpu_ctx)
+    assert np.array_equal(gm, [[3, 11, 19], [9, 65, 185], [3, 11, 19], [5, 61, 181]])
+
+
 def test_degenerate_shapes(gpu_ctx):
     """N = 1, S = 1, empty matrix, empty columns, a set of ALL genes, S above 2^16 (reference benchmark: 61k sets)"""
     P = 400

@@ -187,3 +187,26 @@ def test_r_mean_matches_numpy():
     v = np.random.default_rng(2).normal(size=1001)
     assert abs(O.r_mean(v) - v.mean()) < 1e-15
     assert math.isnan(O.r_mean(np.array([np.nan])))
+
+
+def test_plaid_test_against_scipy_ttests():
+    """plaid.test restatement (R/plaid.R:392-537): its "one" and "lm" legs are textbook t-tests."""
+    from scipy import stats
+    P, N, S = 300, 24, 20
+    X = synth.dense_x_numpy(P, N, seed=5)
+    G = synth.genesets_numpy(P, S, seed=6, size_cap=(5, 60))
+    names = synth.gene_names(P)
+    y = np.arange(N) % 2
+    tab, cols, rows = O.plaid_test(O.Named(X, names, None), y, O.Named(G, names, synth.set_names(S)))
+    assert cols == ["gsetFC", "p.one", "p.two", "p.lm", "p.meta", "q.meta"] and tab.shape == (S, 6)
+    assert np.all(np.diff(tab[:, cols.index("p.meta")]) >= 0)  # sorted by p.meta
+    fc = X[:, y == 1].mean(1) - X[:, y == 0].mean(1)
+    gx = O.plaid(O.Named(X, names, None), O.Named(G, names, None)).mat
+    g = G.toarray() != 0
+    for s in (0, 3, 11):
+        r = rows.index(f"SET{s:05d}")
+        assert abs(tab[r, 1] - stats.ttest_1samp(fc[g[:, s]], 0).pvalue) < 1e-6
+        assert abs(tab[r, 3] - stats.ttest_ind(gx[s, y == 0], gx[s, y == 1], equal_var=False).pvalue) < 1e-10
+    # BH adjustment
+    p = np.array([0.01, 0.04, 0.03, 0.5])
+    assert np.allclose(O.p_adjust_fdr(p), [0.04, 0.04 * 4 / 3, 0.04 * 4 / 3, 0.5])
