@@ -57,7 +57,7 @@ extern "C" {
 #define PLAIDGPU_SSGSEA 3  /* replaid.ssgsea()   R/plaid.R:244-255 */
 #define PLAIDGPU_UCELL 4   /* replaid.ucell()    R/plaid.R:276-282 */
 #define PLAIDGPU_AUCELL 5  /* replaid.aucell()   R/plaid.R:304-309 */
-#define PLAIDGPU_GSVA 6    /* replaid.gsva(rowtf="z")  R/plaid.R:338-363 (rowtf="ecdf" is not on the GPU path) */
+#define PLAIDGPU_GSVA 6    /* replaid.gsva()     R/plaid.R:338-363 (rowtf "z"; "ecdf" single-shard only) */
 
 /* ties.method of base::rank / colRanks (R/plaid.R:589-650) */
 #define PLAIDGPU_TIES_AVERAGE 0
@@ -92,11 +92,15 @@ typedef struct plaidgpu_opts {
   double rmax;           /* replaid.ucell(rmax=), default 1500                   R/plaid.R:276    */
   double auc_max_rank;   /* replaid.aucell(aucMaxRank=); <=0 -> ceiling(0.05*P)  R/plaid.R:304    */
   double tau;            /* replaid.gsva(tau=)                                   R/plaid.R:354-357 */
+  /* (gsva_ecdf below selects rowtf = "ecdf") */
   int64_t nrow_x;        /* nrow(X) used by replaid.sing (rX / nrow(X)); 0 -> X.P  R/plaid.R:216 */
   const double* matg_full_colsums; /* ucell: colSums(matG != 0) over ALL rows of matG [S] (host);
                                       NULL -> taken from plaidgpu_set_genesets      R/plaid.R:280 */
   const double* row_mean;  /* gsva: rowMeans(X) over ALL samples of ALL shards [P] (host); NULL -> this shard only */
   const double* row_sd;    /* gsva: rowSds(X) (sample SD, n-1) [P] (host); NULL -> this shard only  R/plaid.R:343 */
+  int32_t gsva_ecdf;       /* gsva: 1 = rowtf "ecdf" (per-gene ECDF across the samples of THIS call; single
+                              shard only, R/plaid.R:344-346), 0 = rowtf "z" */
+  int32_t _pad2;
 } plaidgpu_opts;
 
 /* cross-shard scalars.  Produced per shard by *_begin (local values), combined by the

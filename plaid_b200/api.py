@@ -395,14 +395,12 @@ def replaid_aucell(X: NamedMatrix, matG: NamedMatrix, aucMaxRank: Optional[float
 
 def replaid_gsva(X: NamedMatrix, matG: NamedMatrix, tau: float = 0.0, rowtf: str = "z", *, ctx=None, out=None):
     """`replaid.gsva(X, matG, tau=0, rowtf="z")` (R/plaid.R:338-363).  `rowtf="ecdf"` ranks every gene
-    ACROSS samples and is not on the GPU path; any other value is the reference's error."""
+    ACROSS the samples of the call (single shard: it needs all samples); any other value is the reference's error."""
     if isinstance(rowtf, (list, tuple)):
         rowtf = rowtf[0]
-    if rowtf == "ecdf":
-        raise NotImplementedError("replaid.gsva(rowtf='ecdf') is not available on the GPU path")
-    if rowtf != "z":
+    if rowtf not in ("z", "ecdf"):
         raise ValueError("Error: unknown row transform" + str(rowtf))  # R/plaid.R:348
-    return _score(X, matG, dict(scorer=L.GSVA, tau=float(tau)), ctx, out)
+    return _score(X, matG, dict(scorer=L.GSVA, tau=float(tau), gsva_ecdf=1 if rowtf == "ecdf" else 0), ctx, out)
 
 
 # ---------------------------------------------------------------------------------------

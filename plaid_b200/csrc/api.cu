@@ -581,8 +581,22 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     // zX <- (X - rowMeans(X)) / (1e-8 + rowSds(X)); rX <- sign(zX) * colRanks(|zX|)   (R/plaid.R:343,351)
     rc = make_dense(c);
     if (rc) return rc;
+    CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
+    CK(c->b_colmax.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
     std::vector<double> mean((size_t)c->P), sd((size_t)c->P);
-    if (opts->row_mean && opts->row_sd) {
+    if (opts->gsva_ecdf) {
+      // zX[g, j] = ecdf(X[g, ])(X[g, j]) = #{samples with X[g, .] <= X[g, j]} / N = max-rank across the
+      // samples / N: transpose, rank every gene's row as a column (ties = max), transpose back  (R/plaid.R:346)
+      const int64_t total = (int64_t)c->P * c->N;
+      CK(c->b_raw.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double)));
+      CK(cudaEventRecord(c->ev[6], c->stream));
+      CK(launch_transpose(c->xx, c->P, c->N, 1.0, c->b_raw.as<double>(), c->stream));  // N x P
+      if (c->N > 0x7fffffff) return fail(c, PLAIDGPU_ERR_ARG, "too many samples for rowtf = ecdf");
+      CK(launch_rank_dense(c->b_raw.as<double>(), (int32_t)c->N, c->P, PLAIDGPU_TIES_MAX, 0, c->b_raw.as<double>(),
+                           nullptr, c->stream));
+      CK(launch_transpose(c->b_raw.as<double>(), c->N, c->P, 1.0 / (double)c->N, c->b_rank.as<double>(), c->stream));
+      c->launches += 3;
+    } else if (opts->row_mean && opts->row_sd) {
       memcpy(mean.data(), opts->row_mean, (size_t)c->P * sizeof(double));
       memcpy(sd.data(), opts->row_sd, (size_t)c->P * sizeof(double));
     } else {  // single shard: both passes locally
@@ -593,14 +607,14 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
       if (rc) return rc;
       for (int32_t r = 0; r < c->P; ++r) sd[r] = c->N > 1 ? sqrt(sd[r] / (double)(c->N - 1)) : NAN;
     }
-    CK(c->b_rowa.reserve((size_t)c->P * sizeof(double)));
-    CK(c->b_rowb.reserve((size_t)c->P * sizeof(double)));
-    CK(cudaMemcpyAsync(c->b_rowa.p, mean.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->b_rowb.p, sd.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
-    CK(c->b_colmax.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
-    CK(cudaEventRecord(c->ev[6], c->stream));
-    CK(launch_ztransform(c->xx, c->P, c->N, c->b_rowa.as<double>(), c->b_rowb.as<double>(), c->b_rank.as<double>(), c->stream));
+    if (!opts->gsva_ecdf) {
+      CK(c->b_rowa.reserve((size_t)c->P * sizeof(double)));
+      CK(c->b_rowb.reserve((size_t)c->P * sizeof(double)));
+      CK(cudaMemcpyAsync(c->b_rowa.p, mean.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->b_rowb.p, sd.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaEventRecord(c->ev[6], c->stream));
+      CK(launch_ztransform(c->xx, c->P, c->N, c->b_rowa.as<double>(), c->b_rowb.as<double>(), c->b_rank.as<double>(), c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));  // mean / sd host vectors die with this scope
     // signed average ranks of the dense z columns, in place (each position is read, then written, by one thread)
     CK(launch_rank_dense(c->b_rank.as<double>(), c->P, c->N, PLAIDGPU_TIES_AVERAGE, 1, c->b_rank.as<double>(),
@@ -933,8 +947,8 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
                          double* out, int64_t chunk) {
   const int64_t N = X->N;
   const int32_t S = c->S;
-  if (opts->scorer == PLAIDGPU_GSVA && !(opts->row_mean && opts->row_sd))
-    return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva: matrix too large for one device pass; pass row_mean / row_sd");
+  if (opts->scorer == PLAIDGPU_GSVA && (opts->gsva_ecdf || !(opts->row_mean && opts->row_sd)))
+    return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva: matrix too large for one device pass (rowtf ecdf needs all samples; rowtf z needs row_mean / row_sd)");
   std::vector<int32_t> pbuf;
   auto sub = [&](int64_t j0, int64_t j1, plaidgpu_matrix* M) {
     *M = *X;

@@ -154,6 +154,8 @@ cudaError_t launch_ztransform(const double* x, int32_t P, int64_t N, const doubl
                               cudaStream_t st);
 cudaError_t launch_densify(const int32_t* xp, const int32_t* xi, const double* xx, int32_t P, int64_t N, double* dense,
                            cudaStream_t st);
+// out (cols x rows, column-major) = scale * transpose(in (rows x cols, column-major))
+cudaError_t launch_transpose(const double* in, int64_t rows, int64_t cols, double scale, double* out, cudaStream_t st);
 // max nnz of any column of a device CSC pointer array
 cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st);
 

@@ -252,6 +252,24 @@ __global__ void __launch_bounds__(256) k_ztransform(const double* __restrict__ x
       z[j * (int64_t)P + r] = (x[j * (int64_t)P + r] - mean[r]) / (1e-8 + sd[r]);
 }
 
+// out[c * R + r] = in[r * C + c] * scale : (R x C column-major ... ) generic tiled transpose of a column-major
+// matrix with `rows` rows and `cols` columns into its transpose (cols x rows, column-major)
+__global__ void __launch_bounds__(256) k_transpose(const double* __restrict__ in, int64_t rows, int64_t cols,
+                                                   double scale, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + tx, c = c0 + k;
+    tile[k][tx] = (r < rows && c < cols) ? in[c * rows + r] : 0.0;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t c = c0 + tx, r = r0 + k;
+    if (r < rows && c < cols) out[r * cols + c] = tile[tx][k] * scale;
+  }
+}
+
 int sm_count() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -364,6 +382,13 @@ cudaError_t launch_ztransform(const double* x, int32_t P, int64_t N, const doubl
 cudaError_t launch_densify(const int32_t* xp, const int32_t* xi, const double* xx, int32_t P, int64_t N, double* dense,
                            cudaStream_t st) {
   return launch_expand_ranks(xp, xi, xx, nullptr, P, N, dense, st);  // same scatter: zeros filled, stored entries placed
+}
+
+cudaError_t launch_transpose(const double* in, int64_t rows, int64_t cols, double scale, double* out, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  dim3 g((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  k_transpose<<<g, 256, 0, st>>>(in, rows, cols, scale, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_max_col_nnz(const int32_t* xp, int64_t N, int32_t* d_res, cudaStream_t st) {

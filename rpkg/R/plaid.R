@@ -116,9 +116,8 @@ replaid.aucell <- function(X, matG, aucMaxRank = ceiling(0.05 * nrow(X))) { # R/
 
 replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1]) {      # R/plaid.R:338-363
   rowtf <- rowtf[1]
-  if (rowtf == "ecdf") stop("replaid.gsva(rowtf = 'ecdf') is not available on the GPU path")
-  if (rowtf != "z") stop("Error: unknown row transform", rowtf)              # R/plaid.R:348
-  .score(X, matG, list(scorer = 6L, tau = as.numeric(tau)))
+  if (!rowtf %in% c("z", "ecdf")) stop("Error: unknown row transform", rowtf) # R/plaid.R:348
+  .score(X, matG, list(scorer = 6L, tau = as.numeric(tau), gsva_ecdf = as.integer(rowtf == "ecdf")))
 }
 
 ## plaid.test (R/plaid.R:392-474): same arguments and result table; the score matrix, the set-wise sums of

@@ -78,6 +78,7 @@ SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim,
   o.rmax = opt_dbl(opts, "rmax", o.rmax);
   o.auc_max_rank = opt_dbl(opts, "auc_max_rank", o.auc_max_rank);
   o.tau = opt_dbl(opts, "tau", o.tau);
+  o.gsva_ecdf = opt_int(opts, "gsva_ecdf", 0);
   o.nrow_x = (int64_t)opt_dbl(opts, "nrow_x", 0.0);
   SEXP cs = list_get(opts, "matg_full_colsums");
   o.matg_full_colsums = cs == R_NilValue ? NULL : REAL(cs);

@@ -30,9 +30,9 @@ def test_header_symbols_all_exported_and_typed():
 
 
 def test_struct_layouts_match_header():
-    # sizes implied by the header (LP64): matrix 4*4+8+3*8 = 48, opts 8*4+4*8+8+3*8 = 96, scalars 5*8+8 = 48
+    # sizes implied by the header (LP64): matrix 4*4+8+3*8 = 48, opts 8*4+4*8+8+3*8+8 = 104, scalars 5*8+8 = 48
     assert C.sizeof(L.Matrix) == 48
-    assert C.sizeof(L.Opts) == 96
+    assert C.sizeof(L.Opts) == 104
     assert C.sizeof(L.Scalars) == 48
     o = L.Opts()
     L.load().plaidgpu_default_opts(C.byref(o))

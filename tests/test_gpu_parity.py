@@ -144,6 +144,10 @@ def test_gsva_z(fixture_mats, golden, gpu_ctx):
     assert rel_err(pb.replaid_gsva(Xg, Gg, tau=0.5, ctx=gpu_ctx).mat, O.replaid_gsva(Xo, Go, tau=0.5).mat) < 1e-9
     with pytest.raises(ValueError):
         pb.replaid_gsva(Xg, Gg, rowtf="nope", ctx=gpu_ctx)
+    # rowtf = "ecdf": per-gene ECDF across samples (ties: every tied sample gets the fraction <= its value)
+    X[9] = np.round(X[9])
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    assert rel_err(pb.replaid_gsva(Xg, Gg, rowtf="ecdf", ctx=gpu_ctx).mat, O.replaid_gsva(Xo, Go, rowtf="ecdf").mat) < 1e-9
 
 
 # ---- ranking: bit-exact, adversarial -----------------------------------------------------------
