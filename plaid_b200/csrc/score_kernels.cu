@@ -52,8 +52,13 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
   double* __restrict__ acc = sacc + (size_t)w * p.Ts;
   char* __restrict__ accb = reinterpret_cast<char*>(acc);
   unsigned char* __restrict__ tag = reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) + (size_t)w * tagw;
-  GeneRec* __restrict__ rec = reinterpret_cast<GeneRec*>(reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) +
-                                                         (size_t)W * tagw) + w * 32;
+  // staged batch, structure-of-arrays (8-byte columns: conflict-free stores, ~1 wavefront per gathered read)
+  unsigned char* __restrict__ recb = reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) + (size_t)W * tagw +
+                                     (size_t)w * 1024;
+  uint2* __restrict__ rec_hdr = reinterpret_cast<uint2*>(recb);          // {overflow offset, chunks}
+  double* __restrict__ rec_x = reinterpret_cast<double*>(recb + 256);
+  uint2* __restrict__ rec_c0 = reinterpret_cast<uint2*>(recb + 512);
+  uint2* __restrict__ rec_c1 = reinterpret_cast<uint2*>(recb + 768);
   for (int l = lane; l < p.Ts; l += 32) acc[l] = 0.0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
@@ -89,9 +94,11 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
       const bool have = nch3 > 0;
       const unsigned m = __ballot_sync(FULL, have);
       if (have) {
-        GeneRec r;
-        r.rest = rest3; r.nchunk = nch3; r.x = x3; r.chunk0 = c03; r.chunk1 = c13;
-        rec[__popc(m & lt)] = r;
+        const int slot = __popc(m & lt);
+        rec_hdr[slot] = make_uint2(rest3, nch3);
+        rec_x[slot] = x3;
+        rec_c0[slot] = c03;
+        rec_c1[slot] = c13;
       }
       qhead = 0;
       qcount = __popc(m);
@@ -142,8 +149,8 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
         }
         const int pos = qhead + __popc(nm & lt);
         if (need && pos < qcount) {
-          const GeneRec r = rec[pos];
-          rest = r.rest; nck = r.nchunk; ck = 0; x = r.x; buf = r.chunk0; nbuf = r.chunk1;
+          const uint2 hd = rec_hdr[pos];
+          rest = hd.x; nck = hd.y; ck = 0; x = rec_x[pos]; buf = rec_c0[pos]; nbuf = rec_c1[pos];
           need = false;
         }
         qhead += __popc(nm);
