@@ -248,32 +248,32 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         const int32_t r = g2x[c->Gi[q]];
         if (r >= 0 && !in_block(r)) setof[fill[r]++] = s;
       }
-    // one 16-byte record per (row, tile): {u32 overflow offset, u16 length, u16 0, u16 entry[4]}; entries
-    // are byte offsets (tile-local set id * 8); lists longer than 4 continue in the overflow array in
+    // one 32-byte record per (row, tile): {u32 overflow offset, u16 length, u16 0, u16 entry[12]}; entries
+    // are byte offsets (tile-local set id * 8); lists longer than 12 continue in the overflow array in
     // chunks of 4 padded with 0xFFFF
     idx.clear();
-    idx.reserve((size_t)nnz_scatter + 16);
-    ptr.assign((size_t)P * T * 4, 0);
+    idx.reserve((size_t)nnz_scatter / 4 + 16);
+    ptr.assign((size_t)P * T * 8, 0);
     for (int32_t r = 0; r < P; ++r) {
       uint32_t e0 = rowcnt[r];
       const uint32_t e1 = rowcnt[r + 1];
       for (int32_t t = 0; t < T; ++t) {
-        uint32_t* rc = ptr.data() + ((size_t)r * T + t) * 4;
+        uint32_t* rc = ptr.data() + ((size_t)r * T + t) * 8;
         const int32_t hi = (t + 1) * Ts;
-        uint16_t in4[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+        uint16_t in12[12];
+        for (int k = 0; k < 12; ++k) in12[k] = 0xFFFFu;
         uint32_t n = 0;
         rc[0] = (uint32_t)idx.size();
         while (e0 < e1 && setof[e0] < hi) {
           const uint16_t off = (uint16_t)((setof[e0] - t * Ts) * 8);
-          if (n < 4) in4[n] = off; else idx.push_back(off);
+          if (n < 12) in12[n] = off; else idx.push_back(off);
           ++n;
           ++e0;
         }
         while (idx.size() & 3) idx.push_back((uint16_t)0xFFFFu);
         if (n > 0xFFFFu) return fail(c, PLAIDGPU_ERR_ARG, "gene-set list too long for one tile");
         rc[1] = n;
-        rc[2] = (uint32_t)in4[0] | ((uint32_t)in4[1] << 16);
-        rc[3] = (uint32_t)in4[2] | ((uint32_t)in4[3] << 16);
+        for (int k = 0; k < 6; ++k) rc[2 + k] = (uint32_t)in12[2 * k] | ((uint32_t)in12[2 * k + 1] << 16);
       }
     }
     for (int k = 0; k < 8; ++k) idx.push_back((uint16_t)0xFFFFu);

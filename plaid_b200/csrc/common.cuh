@@ -35,8 +35,8 @@ struct ScoreParams {
   int32_t P;
   int64_t N;
   // gene-set plan (device): adjacency of every X row, tiled by set range
-  const uint32_t* ptr;  // [P * T] 16-byte tile records {u32 overflow offset, u16 length, u16 0, u16 entry[4]}
-  const uint16_t* idx;  // overflow entries (lists longer than 4), chunks of 4, padded with 0xFFFF;
+  const uint32_t* ptr;  // [P * T] 32-byte tile records {u32 overflow offset, u16 length, u16 0, u16 entry[12]}
+  const uint16_t* idx;  // overflow entries (lists longer than 12), chunks of 4, padded with 0xFFFF;
                         // an entry is the byte offset (tile-local set id * 8) of the accumulator
   const double* inv;    // [S] epilogue scale per set: 1/(n_s + 1e-8) ("mean") or 1 ("sum")
   const double* ns;     // [S] n_s as double

@@ -35,12 +35,14 @@ namespace plaidgpu {
 // registers (entry -> row pointers -> first chunk), so no global-load latency sits on the refill
 // path.  Lists are padded to multiples of 4 entries (0xFFFF): all lanes cross chunk boundaries
 // together and refills happen only there.
-struct __align__(16) GeneRec {
-  uint32_t rest;   // offset of chunk 1 in the overflow array
-  uint32_t nchunk; // number of 4-entry chunks of the list (chunk 0 is inline in the tile record)
-  double x;
-  uint2 chunk0, chunk1;
-};
+
+constexpr int STAGE_BYTES = 1280;  // per warp: 32 staged genes x {hdr, x, 3 chunks} of 8 bytes
+
+// one 32-byte tile record with a single 256-bit load (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void ld_rec32(const void* p, unsigned long long& a, unsigned long long& b,
+                                         unsigned long long& c, unsigned long long& d) {
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
@@ -54,11 +56,12 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
   unsigned char* __restrict__ tag = reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) + (size_t)w * tagw;
   // staged batch, structure-of-arrays (8-byte columns: conflict-free stores, ~1 wavefront per gathered read)
   unsigned char* __restrict__ recb = reinterpret_cast<unsigned char*>(sacc + (size_t)W * p.Ts) + (size_t)W * tagw +
-                                     (size_t)w * 1024;
+                                     (size_t)w * STAGE_BYTES;
   uint2* __restrict__ rec_hdr = reinterpret_cast<uint2*>(recb);          // {overflow offset, chunks}
   double* __restrict__ rec_x = reinterpret_cast<double*>(recb + 256);
   uint2* __restrict__ rec_c0 = reinterpret_cast<uint2*>(recb + 512);
   uint2* __restrict__ rec_c1 = reinterpret_cast<uint2*>(recb + 768);
+  uint2* __restrict__ rec_c2 = reinterpret_cast<uint2*>(recb + 1024);
   for (int l = lane; l < p.Ts; l += 32) acc[l] = 0.0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
@@ -75,42 +78,42 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
     double fb = 0.0;  // f(rank of the zero group): contribution of every implicit zero
     if (GENERAL && p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
     // ---- batch pipeline (lane i prepares entry i of a batch) ---------------------------------
-    // adjacency format: one 16-byte record per (X row, tile) = {overflow offset, list length, 4 inline
-    // entries}; longer lists continue in the overflow array in chunks of 4 (padded with 0xFFFF).  One
-    // scattered 16-byte load therefore yields the pointer AND the first chunk of a (gene, tile) list.
-    const uint4* __restrict__ trec = reinterpret_cast<const uint4*>(p.ptr) + t;
+    // adjacency format: one 32-byte record (= one DRAM/L2 sector) per (X row, tile) = {overflow offset,
+    // list length, 12 inline entries}; longer lists continue in the overflow array in chunks of 4
+    // (padded with 0xFFFF).  One scattered 256-bit load yields the pointer AND the first three chunks of
+    // a (gene, tile) list - most lists are complete with it.
+    const unsigned char* __restrict__ trec = reinterpret_cast<const unsigned char*>(p.ptr) + (size_t)t * 32;
     int64_t ebase = c0;          // first entry of the batch whose (row, value) load is issued next
     int gi1 = -1;                // R1: row index + value loaded
     double x1 = 0.0;
-    uint32_t rest2 = 0, nch2 = 0;  // R2: tile record loaded
-    uint2 c02 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint32_t rest2 = 0, nch2 = 0;  // R2: tile record loaded -> ready to be staged
+    uint2 c02 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), c12 = c02, c22 = c02;
     double x2 = 0.0;
-    uint32_t rest3 = 0, nch3 = 0;  // R3: second chunk loaded -> ready to be staged
-    uint2 c03 = c02, c13 = c02;
-    double x3 = 0.0;
     int qhead = 0, qcount = 0;   // staged batch: records [qhead, qcount) are unassigned (warp-uniform)
 
     auto rotate = [&]() {
-      const bool have = nch3 > 0;
+      const bool have = nch2 > 0;
       const unsigned m = __ballot_sync(FULL, have);
       if (have) {
         const int slot = __popc(m & lt);
-        rec_hdr[slot] = make_uint2(rest3, nch3);
-        rec_x[slot] = x3;
-        rec_c0[slot] = c03;
-        rec_c1[slot] = c13;
+        rec_hdr[slot] = make_uint2(rest2, nch2);
+        rec_x[slot] = x2;
+        rec_c0[slot] = c02;
+        rec_c1[slot] = c12;
+        rec_c2[slot] = c22;
       }
       qhead = 0;
       qcount = __popc(m);
       __syncwarp();
-      rest3 = rest2; nch3 = nch2; x3 = x2; c03 = c02;
-      if (nch3 > 1) c13 = *reinterpret_cast<const uint2*>(p.idx + rest3);
       nch2 = 0;
       if (gi1 >= 0) {
-        const uint4 tr = __ldg(trec + (size_t)gi1 * T);
-        rest2 = tr.x;
-        nch2 = ((tr.y & 0xFFFFu) + 3u) >> 2;
-        c02 = make_uint2(tr.z, tr.w);
+        unsigned long long w0, w1, w2, w3;
+        ld_rec32(trec + (size_t)gi1 * T * 32, w0, w1, w2, w3);
+        rest2 = (uint32_t)w0;
+        nch2 = ((uint32_t)(w0 >> 32) & 0xFFFFu) + 3u >> 2;
+        c02 = make_uint2((uint32_t)w1, (uint32_t)(w1 >> 32));
+        c12 = make_uint2((uint32_t)w2, (uint32_t)(w2 >> 32));
+        c22 = make_uint2((uint32_t)w3, (uint32_t)(w3 >> 32));
         x2 = x1;
         if (GENERAL) x2 = xform_value(p.mode, x1, p.a0, p.a1) - (p.mode >= XF_SING ? fb : 0.0);
       }
@@ -121,8 +124,7 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
       }
       ebase += 32;
     };
-    // prime: after three rotations the first batch is in R3; the fourth stages it
-    rotate();
+    // prime: after two rotations the first batch is in R2; the third stages it
     rotate();
     rotate();
     int remaining = (int)((c1 - c0 + 31) >> 5);  // batches still to be staged (one per further rotation)
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
       // ---- chunk boundary (every 4 steps, all lanes together): advance chunk / take a new gene ----
       ++ck;
       bool need = ck >= nck;
+      bool fresh = false;
       if (!need) {
         buf = nbuf;
         nbuf = nnbuf;
@@ -150,16 +153,17 @@ __global__ void __launch_bounds__(512, 1) k_scatter(const ScoreParams p) {
         const int pos = qhead + __popc(nm & lt);
         if (need && pos < qcount) {
           const uint2 hd = rec_hdr[pos];
-          rest = hd.x; nck = hd.y; ck = 0; x = rec_x[pos]; buf = rec_c0[pos]; nbuf = rec_c1[pos];
+          rest = hd.x; nck = hd.y; ck = 0; x = rec_x[pos]; buf = rec_c0[pos]; nbuf = rec_c1[pos]; nnbuf = rec_c2[pos];
           need = false;
+          fresh = true;
         }
         qhead += __popc(nm);
         __syncwarp();
       }
       const bool alive = ck < nck;
       if (!__any_sync(FULL, alive)) break;  // queue and pipeline are empty too (loop above ran dry)
-      // chunks are fetched two boundaries ahead of their use (a staged record carries the first two)
-      if (alive && ck + 2 < nck) nnbuf = *reinterpret_cast<const uint2*>(p.idx + rest + 4 * (ck + 1));
+      // chunks 3.. live in the overflow array and are fetched two boundaries ahead of their use
+      if (alive && !fresh && ck + 2 < nck) nnbuf = *reinterpret_cast<const uint2*>(p.idx + rest + 4 * (ck - 1));
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
         // branch-free fast path: inactive lanes are pointed at set 0 and simply never win
@@ -284,8 +288,8 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
     if (v >= 1 && v <= 16) warps = v;
   }
   const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin - 1024;  // leave the 1 KB reserve
-  // per warp: Ts fp64 accumulators + Ts byte tags (16-byte aligned) + 32 staged gene records of 32 B
-  int32_t ts_max = (int32_t)((smem_max / warps - 1024 - 16) / 9);
+  // per warp: Ts fp64 accumulators + Ts byte tags (16-byte aligned) + 32 staged genes of 40 B
+  int32_t ts_max = (int32_t)((smem_max / warps - STAGE_BYTES - 16) / 9);
   if (ts_max > 8160) ts_max = 8160;  // tile-local byte offsets are 16-bit (0xFFFF = padding)
   ts_max = (ts_max / 32) * 32;
   if (ts_max > 65536) ts_max = 65536;
@@ -301,7 +305,7 @@ cudaError_t score_configure(int device, int32_t S, int32_t tile_hint, int32_t* T
     if (Ts < 32) Ts = 32;
   }
   cfg->warps = warps;
-  cfg->smem = (size_t)warps * ((size_t)Ts * sizeof(double) + (size_t)((Ts + 15) & ~15) + 1024);
+  cfg->smem = (size_t)warps * ((size_t)Ts * sizeof(double) + (size_t)((Ts + 15) & ~15) + STAGE_BYTES);
   // persistent grid: SM count x resident CTAs per SM
   int per_sm = 0;
   const void* fns[2] = {(const void*)k_scatter<false>, (const void*)k_scatter<true>};
