@@ -215,6 +215,26 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* ctx, const double* x, int32_t S, in
 int plaidgpu_group_moments(plaidgpu_ctx* ctx, const double* x, int32_t S, int64_t N, const int32_t* y,
                            int location, double* out);
 
+/* ---- gene-set ingestion ("next" row f2): host-side, no GPU needed -------------------------- */
+
+/* read.gmt() + gmt2mat() with default arguments (reference R/gmt-utils.R:99-125, 19-66): a GMT text
+ * (name <tab> source <tab> genes...) becomes the genes x sets incidence matrix in gmt2mat's order (sets by
+ * decreasing size, duplicated set names dropped; genes by decreasing membership count, ties by name in
+ * byte order - R uses the session collation, which only permutes rows and never changes a score). */
+typedef struct plaidgpu_gmt plaidgpu_gmt;
+int plaidgpu_gmt_read(const char* path, plaidgpu_gmt** out);
+int plaidgpu_gmt_from_buffer(const char* text, int64_t len, plaidgpu_gmt** out);
+void plaidgpu_gmt_free(plaidgpu_gmt* g);
+int64_t plaidgpu_gmt_num_sets(const plaidgpu_gmt* g);
+int64_t plaidgpu_gmt_num_genes(const plaidgpu_gmt* g);
+int64_t plaidgpu_gmt_nnz(const plaidgpu_gmt* g);
+const char* plaidgpu_gmt_set_name(const plaidgpu_gmt* g, int64_t k);   /* colnames(matG)[k] */
+const char* plaidgpu_gmt_gene_name(const plaidgpu_gmt* g, int64_t k);  /* rownames(matG)[k] */
+/* CSC pattern of matG: Gp int32[num_sets + 1], Gi int32[nnz] (rows ascending within a column) */
+int plaidgpu_gmt_csc(const plaidgpu_gmt* g, int32_t* Gp, int32_t* Gi);
+/* rowmap for plaidgpu_score: intersect(rownames(X), rownames(matG)) + match (R/plaid.R:65-72) */
+int plaidgpu_gmt_rowmap(const plaidgpu_gmt* g, const char* const* x_rownames, int32_t P, int32_t* rowmap);
+
 /* ---- introspection (bench / tests) ------------------------------------------------ */
 
 /* number of kernels launched by this context since creation (or since reset) */

@@ -12,9 +12,11 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def read_gmt(path: str) -> "OrderedDict[str, list[str]]":
-    """`read.gmt` (R/gmt-utils.R:99-125): name <tab> source <tab> genes...; drops "", "NA"."""
-    out: "OrderedDict[str, list[str]]" = OrderedDict()
+def read_gmt(path: str) -> "list[tuple[str, list[str]]]":
+    """`read.gmt` (R/gmt-utils.R:99-125): name <tab> source <tab> genes...; drops "", "NA".
+    Returns (name, genes) pairs in file order: like the R list, duplicated set names are KEPT here
+    (gmt2mat drops them after sorting by size, R/gmt-utils.R:25-26)."""
+    out: "list[tuple[str, list[str]]]" = []
     with open(path, "r", encoding="utf-8", errors="replace") as fh:
         for line in fh:
             line = line.rstrip("\r\n")
@@ -30,14 +32,11 @@ def read_gmt(path: str) -> "OrderedDict[str, list[str]]":
                     continue
                 seen.add(g)
                 gs.append(g)
-            # a list with duplicated names keeps both entries in R; mimic with a suffix-free
-            # overwrite guard: later duplicates are dropped by gmt2mat anyway (:26)
-            if name not in out:
-                out[name] = gs
+            out.append((name, gs))
     return out
 
 
-def gmt2mat(gmt: "dict[str, list[str]]"):
+def gmt2mat(gmt):
     """`gmt2mat` (R/gmt-utils.R:19-66) with default arguments.
 
     Returns (csc_matrix genes x sets of 1.0, rownames, colnames).
@@ -46,9 +45,15 @@ def gmt2mat(gmt: "dict[str, list[str]]"):
     session collation; plain code-point order is used here — row order never affects
     scores because plaid() matches rows by name, `R/plaid.R:65-72`).
     """
-    names = list(gmt.keys())
-    order = sorted(range(len(names)), key=lambda k: -len(gmt[names[k]]))  # stable
-    names = [names[k] for k in order]
+    pairs = list(gmt.items()) if isinstance(gmt, dict) else list(gmt)
+    pairs.sort(key=lambda kv: -len(kv[1]))  # stable: order(-sapply(gmt, length))   (:25)
+    seen_names, uniq = set(), []
+    for n, gs in pairs:  # gmt[!duplicated(names(gmt))]   (:26): the largest set of a duplicated name survives
+        if n not in seen_names:
+            seen_names.add(n)
+            uniq.append((n, gs))
+    names = [n for n, _ in uniq]
+    gmt = dict(uniq)
     cnt = Counter(g for n in names for g in gmt[n])
     bg = sorted(cnt.keys())  # table(): sorted level names
     bg.sort(key=lambda g: -cnt[g])  # sort(decreasing=TRUE), stable

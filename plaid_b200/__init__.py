@@ -5,9 +5,9 @@ this package is the host-side mirror of the reference's R interface used by test
 Importing the package does not need a GPU; calling any scorer does (no CPU fallback).
 """
 from .api import (Context, DeviceCSC, DeviceDense, NamedMatrix, chunked_crossprod, colranks, default_context,
-                  group_moments, make_rowmap, normalize_medians, plaid, plaid_test, replaid_aucell, replaid_gsva, replaid_scse, replaid_sing,
+                  gmt2mat_file, group_moments, make_rowmap, normalize_medians, plaid, plaid_test, replaid_aucell, replaid_gsva, replaid_scse, replaid_sing,
                   replaid_ssgsea, replaid_ucell, sparse_colranks)
 
 __all__ = ["Context", "DeviceCSC", "DeviceDense", "NamedMatrix", "chunked_crossprod", "colranks",
-           "default_context", "group_moments", "make_rowmap", "normalize_medians", "plaid", "plaid_test", "replaid_aucell", "replaid_gsva", "replaid_scse",
+           "default_context", "gmt2mat_file", "group_moments", "make_rowmap", "normalize_medians", "plaid", "plaid_test", "replaid_aucell", "replaid_gsva", "replaid_scse",
            "replaid_sing", "replaid_ssgsea", "replaid_ucell", "sparse_colranks"]

@@ -59,6 +59,16 @@ SYMBOLS = {
     "plaidgpu_colranks": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "plaidgpu_group_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "plaidgpu_normalize_medians": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "plaidgpu_gmt_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "plaidgpu_gmt_from_buffer": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "plaidgpu_gmt_free": (None, [C.c_void_p]),
+    "plaidgpu_gmt_num_sets": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_gmt_num_genes": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_gmt_nnz": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_gmt_set_name": (C.c_char_p, [C.c_void_p, C.c_int64]),
+    "plaidgpu_gmt_gene_name": (C.c_char_p, [C.c_void_p, C.c_int64]),
+    "plaidgpu_gmt_csc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plaidgpu_gmt_rowmap": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int32, C.c_void_p]),
     "plaidgpu_launch_count": (C.c_int64, [C.c_void_p]),
     "plaidgpu_reset_launch_count": (None, [C.c_void_p]),
     "plaidgpu_last_kernel_ms": (C.c_double, [C.c_void_p, C.c_int]),

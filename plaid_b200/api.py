@@ -507,3 +507,29 @@ def plaid_test(X: NamedMatrix, y, G: NamedMatrix, gsetX: Optional[NamedMatrix] =
         oo = np.argsort(tab[:, cols.index(sort_by)], kind="stable")
         tab, rows = tab[oo], [rows[k] for k in oo]
     return tab, cols, rows
+
+
+# ---------------------------------------------------------------------------------------
+# gene-set ingestion (host-side C++ behind the same ABI; needs no GPU)
+# ---------------------------------------------------------------------------------------
+def gmt2mat_file(path: str) -> NamedMatrix:
+    """`gmt2mat(read.gmt(path))` (R/gmt-utils.R:99-125, 19-66) in one call: genes x sets csc_matrix of ones
+    with gmt2mat's row / column order."""
+    lib = L.load()
+    h = C.c_void_p()
+    rc = lib.plaidgpu_gmt_read(path.encode(), C.byref(h))
+    if rc != L.OK:
+        raise L.PlaidGpuError(rc, f"cannot read GMT file {path!r}")
+    try:
+        S, P, nnz = lib.plaidgpu_gmt_num_sets(h), lib.plaidgpu_gmt_num_genes(h), lib.plaidgpu_gmt_nnz(h)
+        gp = np.empty(S + 1, dtype=np.int32)
+        gi = np.empty(max(nnz, 1), dtype=np.int32)
+        rc = lib.plaidgpu_gmt_csc(h, gp.ctypes.data, gi.ctypes.data)
+        if rc != L.OK:
+            raise L.PlaidGpuError(rc, "plaidgpu_gmt_csc failed")
+        sets = [lib.plaidgpu_gmt_set_name(h, k).decode() for k in range(S)]
+        genes = [lib.plaidgpu_gmt_gene_name(h, k).decode() for k in range(P)]
+        G = sp.csc_matrix((np.ones(nnz), gi[:nnz], gp), shape=(P, S))
+        return NamedMatrix(G, genes, sets)
+    finally:
+        lib.plaidgpu_gmt_free(h)

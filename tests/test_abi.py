@@ -77,3 +77,34 @@ def test_rowmap_semantics():
     from plaid_b200 import make_rowmap
     rm = make_rowmap(["a", "b", "a", "c", "zz"], ["c", "a", "q", "a"])
     assert rm.tolist() == [1, -1, -1, 0, -1]  # first occurrence on both sides (R/plaid.R:65-72)
+
+
+def test_gmt_ingestion_matches_oracle(tmp_path):
+    """read.gmt + gmt2mat in C++ behind the ABI (scope row f2) vs the oracle restatement, on the reference's
+    bundled hallmarks.gmt and on an adversarial file (comments, CRLF, duplicated set names, NA, blanks)."""
+    import ctypes as C
+    from oracle.gmt import gmt2mat, read_gmt
+    from plaid_b200 import gmt2mat_file
+    path = os.path.join(ROOT, "tests", "golden", "hallmarks.gmt")
+    got = gmt2mat_file(path)
+    D, rn, cn = gmt2mat(read_gmt(path))
+    assert got.shape == (4386, 50) == D.shape  # vignette known answer
+    assert got.colnames == cn and got.rownames == rn
+    assert (got.mat != D).nnz == 0
+    tricky = tmp_path / "t.gmt"
+    tricky.write_bytes(b"# comment\nS1\tsrc\tA\tB\tNA\tB\t\tC D\r\nS2\tsrc\tB\nS1\tdup\tZ\tY\tX\tW\tV\tU\nS3\tsrc\n")
+    got = gmt2mat_file(str(tricky))
+    D, rn, cn = gmt2mat(read_gmt(str(tricky)))
+    assert got.colnames == cn and got.rownames == rn and (got.mat != D).nnz == 0
+    # rowmap: first occurrence of a duplicated X rowname wins, unknown names -> -1
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.plaidgpu_gmt_read(str(tricky).encode(), C.byref(h)) == 0
+    last = got.rownames[-1]
+    assert last != "B"
+    names = [b"B", b"nope", b"B", last.encode()]
+    arr = (C.c_char_p * 4)(*names)
+    rm = np.empty(4, dtype=np.int32)
+    assert lib.plaidgpu_gmt_rowmap(h, arr, 4, rm.ctypes.data) == 0
+    assert rm.tolist() == [got.rownames.index("B"), -1, -1, len(got.rownames) - 1]
+    lib.plaidgpu_gmt_free(h)
