@@ -759,14 +759,12 @@ __global__ void k_minmax_fin(const unsigned long long* res, double* out) {
 cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
                             double* med_nz, double* colmin, int* d_fail, int64_t* d_list, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device (a process may drive several GPUs): cheap, so set on every launch
     cudaError_t e = cudaFuncSetAttribute(k_colstats, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(StatsSmem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_colstats_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats2Smem));
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
