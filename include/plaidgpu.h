@@ -57,7 +57,11 @@ extern "C" {
 #define PLAIDGPU_SSGSEA 3  /* replaid.ssgsea()   R/plaid.R:244-255 */
 #define PLAIDGPU_UCELL 4   /* replaid.ucell()    R/plaid.R:276-282 */
 #define PLAIDGPU_AUCELL 5  /* replaid.aucell()   R/plaid.R:304-309 */
-#define PLAIDGPU_GSVA 6    /* replaid.gsva()     R/plaid.R:338-363 (rowtf "z"; "ecdf" single-shard only) */
+#define PLAIDGPU_GSVA 6    /* replaid.gsva()     R/plaid.R:338-363 */
+
+#define PLAIDGPU_ROWTF_Z 0
+#define PLAIDGPU_ROWTF_ECDF 1
+#define PLAIDGPU_ROWTF_DONE 2
 
 /* ties.method of base::rank / colRanks (R/plaid.R:589-650) */
 #define PLAIDGPU_TIES_AVERAGE 0
@@ -98,8 +102,11 @@ typedef struct plaidgpu_opts {
                                       NULL -> taken from plaidgpu_set_genesets      R/plaid.R:280 */
   const double* row_mean;  /* gsva: rowMeans(X) over ALL samples of ALL shards [P] (host); NULL -> this shard only */
   const double* row_sd;    /* gsva: rowSds(X) (sample SD, n-1) [P] (host); NULL -> this shard only  R/plaid.R:343 */
-  int32_t gsva_ecdf;       /* gsva: 1 = rowtf "ecdf" (per-gene ECDF across the samples of THIS call; single
-                              shard only, R/plaid.R:344-346), 0 = rowtf "z" */
+  int32_t gsva_ecdf;       /* gsva row transform: PLAIDGPU_ROWTF_Z (0) = rowtf "z"; PLAIDGPU_ROWTF_ECDF (1) = rowtf
+                              "ecdf", per-gene ECDF across the samples of THIS call (one shard holds all
+                              samples, R/plaid.R:344-346); PLAIDGPU_ROWTF_DONE (2) = X already holds the
+                              row-transformed values (column shards: plaidgpu_row_ecdf after the
+                              column -> row exchange, see plaid_b200/sharded.py gsva_shard) */
   int32_t _pad2;
 } plaidgpu_opts;
 
@@ -185,6 +192,14 @@ int plaidgpu_crossprod(plaidgpu_ctx* ctx, const plaidgpu_matrix* Y, const int32_
  * The caller adds the shards' vectors, divides by N_total (resp. N_total - 1, sqrt) and passes the
  * results as opts.row_mean / opts.row_sd.  out: host double[P]. */
 int plaidgpu_row_moments(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, const double* mean, double* out);
+
+/* replaid.gsva(rowtf = "ecdf") on column shards (R/plaid.R:346: apply(X, 1, function(x) ecdf(x)(x))).
+ * The ECDF of a gene runs ACROSS samples, the one axis the path is sharded on, so the shards exchange
+ * (all-to-all) their dense blocks into row blocks first.  x: N x rows col-major, i.e. the N samples of
+ * every gene of this rank's row block are contiguous; replaced in place by
+ * #{samples with value <= x} / N.  The caller exchanges the result back and scores the shard with
+ * opts.gsva_ecdf = PLAIDGPU_ROWTF_DONE.  location: where x lives. */
+int plaidgpu_row_ecdf(plaidgpu_ctx* ctx, double* x, int64_t N, int32_t rows, int location);
 
 /* ---- ranking ---------------------------------------------------------------------- */
 

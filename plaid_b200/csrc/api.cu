@@ -584,7 +584,12 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     CK(c->b_rank.reserve(std::max<int64_t>(c->nnz, 1) * sizeof(double)));
     CK(c->b_colmax.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
     std::vector<double> mean((size_t)c->P), sd((size_t)c->P);
-    if (opts->gsva_ecdf) {
+    if (opts->gsva_ecdf == PLAIDGPU_ROWTF_DONE) {
+      // the caller applied the row transform across all shards (plaidgpu_row_ecdf after the
+      // column -> row exchange, or its own z): rank the columns of X as they are
+      CK(cudaEventRecord(c->ev[6], c->stream));
+      CK(cudaMemcpyAsync(c->b_rank.p, c->xx, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    } else if (opts->gsva_ecdf) {
       // zX[g, j] = ecdf(X[g, ])(X[g, j]) = #{samples with X[g, .] <= X[g, j]} / N = max-rank across the
       // samples / N: transpose, rank every gene's row as a column (ties = max), transpose back  (R/plaid.R:346)
       const int64_t total = (int64_t)c->P * c->N;
@@ -607,7 +612,7 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
       if (rc) return rc;
       for (int32_t r = 0; r < c->P; ++r) sd[r] = c->N > 1 ? sqrt(sd[r] / (double)(c->N - 1)) : NAN;
     }
-    if (!opts->gsva_ecdf) {
+    if (opts->gsva_ecdf == PLAIDGPU_ROWTF_Z) {
       CK(c->b_rowa.reserve((size_t)c->P * sizeof(double)));
       CK(c->b_rowb.reserve((size_t)c->P * sizeof(double)));
       CK(cudaMemcpyAsync(c->b_rowa.p, mean.data(), (size_t)c->P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -947,7 +952,8 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
                          double* out, int64_t chunk) {
   const int64_t N = X->N;
   const int32_t S = c->S;
-  if (opts->scorer == PLAIDGPU_GSVA && (opts->gsva_ecdf || !(opts->row_mean && opts->row_sd)))
+  if (opts->scorer == PLAIDGPU_GSVA && opts->gsva_ecdf != PLAIDGPU_ROWTF_DONE &&
+      (opts->gsva_ecdf || !(opts->row_mean && opts->row_sd)))
     return fail(c, PLAIDGPU_ERR_ARG, "replaid.gsva: matrix too large for one device pass (rowtf ecdf needs all samples; rowtf z needs row_mean / row_sd)");
   std::vector<int32_t> pbuf;
   auto sub = [&](int64_t j0, int64_t j1, plaidgpu_matrix* M) {
@@ -1092,6 +1098,34 @@ int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double
   rc = make_dense(c);
   if (rc) return rc;
   return row_moments(c, mean, out);
+}
+
+int plaidgpu_row_ecdf(plaidgpu_ctx* c, double* x, int64_t N, int32_t rows, int location) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!x && N > 0 && rows > 0) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (N < 0 || rows < 0 || N > 0x7fffffff) return fail(c, PLAIDGPU_ERR_ARG, "bad dimensions for row ecdf");
+  CK(cudaSetDevice(c->device));
+  c->in_call = false;
+  c->computed = false;
+  const int64_t total = N * (int64_t)rows;
+  if (total == 0) return PLAIDGPU_OK;
+  const double* src = nullptr;
+  int rc = to_device<double>(c, x, (size_t)total, location, c->b_xx, &src);
+  if (rc) return rc;
+  double* d = const_cast<double*>(src);
+  // every gene's samples are one column of the N x rows matrix: max-rank / N  (R/plaid.R:346)
+  CK(cudaEventRecord(c->ev[6], c->stream));
+  CK(launch_rank_dense(d, (int32_t)N, rows, PLAIDGPU_TIES_MAX, 0, d, nullptr, c->stream));
+  CK(launch_xform_dense(d, d, total, XF_SCALE, 1.0 / (double)N, 0.0, c->stream));
+  c->launches += 2;
+  CK(cudaEventRecord(c->ev[7], c->stream));
+  if (location == PLAIDGPU_HOST)
+    CK(cudaMemcpyAsync(x, d, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+  c->ms[3] = ms;
+  return PLAIDGPU_OK;
 }
 
 // -----------------------------------------------------------------------------------------

@@ -22,7 +22,8 @@ enum XformMode : int {
   XF_SSGSEA = 4,    // r^(1+a1) / a0 - 0.5, a0 = max(r^(1+a1))            (R/plaid.R:246-251)
   XF_UCELL = 5,     // min(a0 - r, a1), a0 = max(r), a1 = rmax + 1         (R/plaid.R:278)
   XF_AUCELL = 6,    // 1.08 * max((r - (a0 - a1)) / a1, 0), a1 = aucMaxRank (R/plaid.R:306)
-  XF_GSVA = 7       // r / a0, then sign * |.|^(1 + a1) when a1 > 0 (dense only)  (R/plaid.R:352-357)
+  XF_GSVA = 7,      // r / a0, then sign * |.|^(1 + a1) when a1 > 0 (dense only)  (R/plaid.R:352-357)
+  XF_SCALE = 8      // v * a0: max-rank -> ecdf value, a0 = 1 / N                 (R/plaid.R:346)
 };
 
 struct ScoreParams {
@@ -168,6 +169,7 @@ __device__ __forceinline__ double xform_value(int mode, double v, double a0, dou
     case XF_SSGSEA: return (a1 != 0.0 ? pow(v, 1.0 + a1) : v) / a0 - 0.5;
     case XF_UCELL: return fmin(a0 - v, a1);
     case XF_AUCELL: return 1.08 * fmax((v - (a0 - a1)) / a1, 0.0);
+    case XF_SCALE: return v * a0;
     case XF_GSVA: {
       const double r = v / a0;
       return a1 > 0.0 ? copysign(pow(fabs(r), 1.0 + a1), r) * (r == 0.0 ? 0.0 : 1.0) : r;

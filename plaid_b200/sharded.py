@@ -6,7 +6,11 @@ collective.  What does couple the shards are a handful of scalars (SURVEY.md §8
   * min / max of X                      (replaid.scse auto removeLog2, R/plaid.R:160-161)
   * max(rX)                             (ssgsea / ucell / aucell, R/plaid.R:251,278,306)
   * min(scores) and mean(col medians)   (normalize_medians, R/plaid.R:557,572)
-They are exchanged with torch.distributed (NCCL on GPUs, gloo in the CPU tests): all-reduce
+replaid.gsva is the exception: its row transform runs ACROSS samples.  rowtf "z"
+needs per-gene sums (all-reduce of P doubles, twice); rowtf "ecdf" needs every gene's values over all
+samples, so the dense shards are re-partitioned column blocks -> row blocks with an all-to-all, ranked
+(plaidgpu_row_ecdf) and sent back — `gsva_shard` below.
+The scalars are exchanged with torch.distributed (NCCL on GPUs, gloo in the CPU tests): all-reduce
 (min / max) of single doubles and an all-gather of the per-column medians, which every rank
 then combines in GLOBAL COLUMN ORDER (plaidgpu_combine_medians), so results are bit-identical
 for any number of shards.
@@ -33,6 +37,56 @@ class LocalComm:
 
     def allgather_vec(self, v: np.ndarray) -> np.ndarray:
         return v
+
+    def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
+        return v
+
+    def alltoall(self, parts):
+        return list(parts)
+
+
+class ThreadComm:
+    """Shards driven by threads of ONE process (one context each; ctypes calls release the GIL).
+    `ThreadComm.group(world)` returns the `world` endpoints; every collective is a rendezvous on a
+    shared slot table, combined in rank order."""
+
+    def __init__(self, shared, rank):
+        self._s, self.rank, self.world = shared, rank, shared["world"]
+
+    @classmethod
+    def group(cls, world: int):
+        import threading
+        shared = {"world": world, "slots": [None] * world, "barrier": threading.Barrier(world)}
+        return [cls(shared, r) for r in range(world)]
+
+    def _exchange(self, v):
+        s = self._s
+        s["slots"][self.rank] = v
+        s["barrier"].wait()
+        vals = list(s["slots"])
+        s["barrier"].wait()
+        return vals
+
+    def allreduce_min(self, v: float) -> float:
+        return min(self._exchange(v))
+
+    def allreduce_max(self, v: float) -> float:
+        return max(self._exchange(v))
+
+    def allgather_vec(self, v: np.ndarray) -> np.ndarray:
+        return np.concatenate(self._exchange(np.asarray(v, dtype=np.float64)))
+
+    def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
+        vals = self._exchange(np.asarray(v, dtype=np.float64))
+        acc = vals[0].copy()
+        for w in vals[1:]:
+            acc += w
+        return acc
+
+    def alltoall(self, parts):
+        """parts[q] goes to rank q; returns what every rank r sent to this rank, in rank order"""
+        table = self._exchange(list(parts))
+        return [table[r][self.rank] for r in range(self.world)]
 
 
 class TorchComm:
@@ -72,6 +126,41 @@ class TorchComm:
         dist.all_gather(parts, buf, group=self.group)
         return np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)]) if sizes else v
 
+    def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
+        """element-wise sum over ranks, added in RANK ORDER on every rank (not a tree all-reduce), so
+        all ranks hold the same bits"""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        flat = self.allgather_vec(v).reshape(self.world, v.size)
+        acc = flat[0].copy()
+        for r in range(1, self.world):
+            acc += flat[r]
+        return acc.reshape(v.shape)
+
+    def alltoall(self, parts):
+        """parts[q] (2-D float64, rows fixed by the receiver's row block) goes to rank q.  NCCL: one
+        all_to_all over NVLink; gloo (CPU tests) has no all-to-all, so pairwise send / recv."""
+        torch, dist = self.torch, self.dist
+        shapes = np.array([[p.shape[0], p.shape[1]] for p in parts], dtype=np.float64).ravel()
+        allshapes = self.allgather_vec(shapes).reshape(self.world, self.world, 2).astype(np.int64)
+        ins = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float64)).to(self.device) for p in parts]
+        outs = [torch.empty((int(allshapes[r, self.rank, 0]), int(allshapes[r, self.rank, 1])), dtype=torch.float64,
+                            device=self.device) for r in range(self.world)]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all(outs, ins, group=self.group)
+        else:
+            outs[self.rank].copy_(ins[self.rank])
+            reqs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                if ins[r].numel():
+                    reqs.append(dist.isend(ins[r], dst=dist.get_global_rank(self.group, r) if self.group else r, group=self.group))
+                if outs[r].numel():
+                    reqs.append(dist.irecv(outs[r], src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group))
+            for q in reqs:
+                q.wait()
+        return [o.cpu().numpy() for o in outs]
+
 
 def combine_scalars(comm, local: L.Scalars) -> L.Scalars:
     """step 2 of the protocol in include/plaidgpu.h: x_min (min), x_max (max), rank_max (max)."""
@@ -101,7 +190,7 @@ def score_shard(ctx, comm, M: L.Matrix, rowmap: np.ndarray, opts: L.Opts, out_pt
     ctx.check(lib.plaidgpu_score_begin(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(opts), C.byref(local)))
     scal = combine_scalars(comm, local)
     ctx.check(lib.plaidgpu_score_compute(ctx.h, C.byref(scal), out_ptr))
-    needs_norm = (opts.scorer in (L.SSGSEA, L.UCELL, L.AUCELL)) or (opts.scorer == L.PLAID and opts.normalize)
+    needs_norm = (opts.scorer in (L.SSGSEA, L.UCELL, L.AUCELL, L.GSVA)) or (opts.scorer == L.PLAID and opts.normalize)
     if needs_norm:
         ma = np.empty(n_cols, dtype=np.float64)
         mz = np.empty(n_cols, dtype=np.float64)
@@ -116,6 +205,67 @@ def shard_columns(n_total: int, world: int, rank: int):
     base, rem = divmod(n_total, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+# ---------------------------------------------------------------------------------------
+# replaid.gsva on column shards
+# ---------------------------------------------------------------------------------------
+def exchange_to_rows(comm, Xd: np.ndarray):
+    """Column shard (P x n_r) -> this rank's row block over ALL samples.  Returns (block, counts):
+    block is (P_q, N) C-contiguous — the memory layout of an N x P_q column-major matrix, every gene's
+    samples contiguous in global column order — and counts[r] = n_r."""
+    P = Xd.shape[0]
+    parts = []
+    for q in range(comm.world):
+        g0, g1 = shard_columns(P, comm.world, q)
+        parts.append(np.ascontiguousarray(Xd[g0:g1, :], dtype=np.float64))
+    recv = comm.alltoall(parts)
+    return np.ascontiguousarray(np.concatenate(recv, axis=1)), [int(p.shape[1]) for p in recv]
+
+
+def exchange_to_columns(comm, block: np.ndarray, counts):
+    """inverse of exchange_to_rows: row block (P_q, N) -> column shard (P, n_r), Fortran order"""
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    parts = [np.ascontiguousarray(block[:, offs[r]:offs[r + 1]]) for r in range(comm.world)]
+    recv = comm.alltoall(parts)
+    return np.asfortranarray(np.concatenate(recv, axis=0))
+
+
+def gsva_shard(ctx, comm, Xd: np.ndarray, rowmap: np.ndarray, opts: L.Opts, out_ptr: int, rowtf: str = "z"):
+    """replaid.gsva(X, matG, tau, rowtf) (R/plaid.R:338-363) for this rank's dense column shard Xd (P x n_r).
+      rowtf "z":    rowMeans / rowSds over all shards = two all-reduces of P doubles around
+                    plaidgpu_row_moments (two-pass SD like mat.rowsds, R/plaid.R:365-370);
+      rowtf "ecdf": all-to-all into row blocks, plaidgpu_row_ecdf, all-to-all back.
+    Then the ordinary sharded protocol (score_shard) ranks and scores the columns."""
+    lib = ctx.lib
+    Xd = np.asfortranarray(Xd, dtype=np.float64)
+    P, n = Xd.shape
+    keep = []
+    if rowtf == "ecdf":
+        block, counts = exchange_to_rows(comm, Xd)
+        rows, N = block.shape
+        ctx.check(lib.plaidgpu_row_ecdf(ctx.h, block.ctypes.data, N, rows, L.HOST))
+        Xd = exchange_to_columns(comm, block, counts)
+        opts.gsva_ecdf = L.ROWTF_DONE
+    elif rowtf == "z":
+        M = L.Matrix()
+        M.kind, M.location, M.P, M.N, M.x = L.DENSE, L.HOST, P, n, Xd.ctypes.data
+        N = int(round(comm.allgather_vec(np.array([float(n)])).sum()))
+        part = np.empty(P)
+        ctx.check(lib.plaidgpu_row_moments(ctx.h, C.byref(M), None, part.ctypes.data))
+        mean = comm.allreduce_sum_vec(part) / N
+        ctx.check(lib.plaidgpu_row_moments(ctx.h, C.byref(M), mean.ctypes.data, part.ctypes.data))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sd = np.sqrt(comm.allreduce_sum_vec(part) / (N - 1)) if N > 1 else np.full(P, np.nan)
+        keep += [mean, sd]
+        opts.row_mean, opts.row_sd = mean.ctypes.data, sd.ctypes.data
+        opts.gsva_ecdf = L.ROWTF_Z
+    else:
+        raise ValueError('rowtf must be "z" or "ecdf"')
+    M = L.Matrix()
+    M.kind, M.location, M.P, M.N, M.x = L.DENSE, L.HOST, P, n, Xd.ctypes.data
+    opts.scorer = L.GSVA
+    return score_shard(ctx, comm, M, rowmap, opts, out_ptr, n)
 
 
 def score_multi(ctxs, mats, rowmap: np.ndarray, opts_list, out_ptrs, n_cols):

@@ -343,6 +343,58 @@ def test_sharded_protocol_is_shard_count_invariant():
             assert np.array_equal(np.concatenate(outs, axis=1), whole)
 
 
+def test_gsva_on_column_shards():
+    """replaid.gsva on 2 and 3 ragged column shards (threads, one context each): rowtf "ecdf" re-partitions
+    the dense shards into row blocks (all-to-all), ranks each gene across ALL samples (plaidgpu_row_ecdf)
+    and sends them back -> bit-identical to the one-shard call; rowtf "z" all-reduces the row sums
+    (R/plaid.R:343-346)."""
+    import threading
+    from plaid_b200 import _lib as L, sharded
+    from plaid_b200.api import _opts
+    P, N, S = 900, 53, 700
+    Draw = synth.dense_x_numpy(P, N, seed=61)
+    Dtie = np.round(Draw, 1)  # ties across samples and genes; only for ecdf: with rounded data some values EQUAL
+    # their row mean, z is then +-1e-15 noise whose sign (hence signed rank) depends on the summation order
+    G = synth.genesets_numpy(P, S, seed=62, size_cap=(5, 150))
+    names = synth.gene_names(P)
+    rowmap = pb.make_rowmap(names, names)
+    ctxs = [pb.Context(0) for _ in range(3)]
+    for c in ctxs:
+        c.set_genesets(G)
+    Go = O.Named(G, names, [f"s{k}" for k in range(S)])
+    for rowtf, tau in (("ecdf", 0.0), ("z", 0.0), ("ecdf", 0.5)):
+        D = Dtie if rowtf == "ecdf" else Draw
+        Xo = O.Named(D, names, [f"c{k}" for k in range(N)])
+        whole = pb.replaid_gsva(pb.NamedMatrix(D, names), pb.NamedMatrix(G, names), tau=tau, rowtf=rowtf, ctx=ctxs[0]).mat
+        assert rel_err(whole, O.replaid_gsva(Xo, Go, tau=tau, rowtf=rowtf).mat) < 1e-9
+        for world in (2, 3):
+            comms = sharded.ThreadComm.group(world)
+            spans = [sharded.shard_columns(N, world, r) for r in range(world)]
+            outs = [np.empty((S, hi - lo), order="F") for lo, hi in spans]
+            errs = []
+
+            def run(r):
+                try:
+                    lo, hi = spans[r]
+                    o = _opts(ctxs[r].lib, scorer=L.GSVA, out_location=L.HOST, tau=tau)
+                    sharded.gsva_shard(ctxs[r], comms[r], D[:, lo:hi], rowmap, o, outs[r].ctypes.data, rowtf=rowtf)
+                except Exception as e:  # pragma: no cover
+                    errs.append(e)
+                    comms[r]._s["barrier"].abort()
+
+            ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join(timeout=120)
+            assert not errs, errs
+            got = np.concatenate(outs, axis=1)
+            if rowtf == "ecdf":
+                assert np.array_equal(got, whole)
+            else:  # row sums are added per shard: last-bit differences in z may move a rank by a tie
+                assert rel_err(got, whole) < 1e-9
+
+
 def test_column_chunked_host_path_is_bit_identical(monkeypatch):
     """outputs larger than the device budget are scored in column chunks (two passes when normalised);
     forced here with a tiny budget: results must equal the one-pass results bit for bit"""

@@ -76,3 +76,74 @@ def test_shard_columns_cover_everything():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+# ---- replaid.gsva on column shards: the column -> row exchange ---------------
+def _ecdf_rows(block):
+    """ecdf(x)(x) of every row (R/plaid.R:346), numpy"""
+    return np.stack([(r[None, :] <= r[:, None]).sum(axis=1) / r.size for r in block])
+
+
+def _exchange_worker(rank, world, port, P, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = sharded.TorchComm(device="cpu")
+    X = np.round(np.random.default_rng(7).normal(size=(P, n_total)), 1)  # rounding: ties across samples
+    lo, hi = sharded.shard_columns(n_total, world, rank)
+    block, counts = sharded.exchange_to_rows(comm, X[:, lo:hi])
+    g0, g1 = sharded.shard_columns(P, world, rank)
+    ok_rows = np.array_equal(block, X[g0:g1, :]) and block.flags.c_contiguous
+    back = sharded.exchange_to_columns(comm, _ecdf_rows(block), counts)
+    ok_back = np.array_equal(back, _ecdf_rows(X)[:, lo:hi]) and back.flags.f_contiguous
+    sums = comm.allreduce_sum_vec(X[:, lo:hi].sum(axis=1))
+    ref = X[:, :sharded.shard_columns(n_total, world, 0)[1]].sum(axis=1)
+    for r in range(1, world):
+        a, b = sharded.shard_columns(n_total, world, r)
+        ref = ref + X[:, a:b].sum(axis=1)
+    q.put((rank, ok_rows, ok_back, counts, bool(np.array_equal(sums, ref))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_exchange_round_trip():
+    P, n_total, world = 37, 23, 2  # both axes ragged
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, P, n_total, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] and r[2] and r[4]
+        assert r[3] == [12, 11]
+
+
+def test_thread_comm_collectives():
+    import threading
+    world = 3
+    comms = sharded.ThreadComm.group(world)
+    X = np.random.default_rng(3).normal(size=(10, 8))
+    out = [None] * world
+
+    def run(r):
+        c = comms[r]
+        lo, hi = sharded.shard_columns(8, world, r)
+        block, counts = sharded.exchange_to_rows(c, X[:, lo:hi])
+        back = sharded.exchange_to_columns(c, block * 2.0, counts)
+        out[r] = (c.allreduce_min(float(r)), c.allreduce_max(float(r)), c.allgather_vec(np.array([float(r)])),
+                  c.allreduce_sum_vec(np.array([1.0, r])), block, back, lo, hi)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=60)
+    for r, o in enumerate(out):
+        g0, g1 = sharded.shard_columns(10, world, r)
+        assert o[0] == 0.0 and o[1] == 2.0 and list(o[2]) == [0.0, 1.0, 2.0] and list(o[3]) == [3.0, 3.0]
+        assert np.array_equal(o[4], X[g0:g1]) and np.array_equal(o[5], 2.0 * X[:, o[6]:o[7]])
