@@ -179,6 +179,16 @@ int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double
                              const double* med_nz, int64_t N_total, plaidgpu_scalars* scal);
 int plaidgpu_score_finish(plaidgpu_ctx* ctx, const plaidgpu_scalars* scal, double* out);
 
+/* Tiled egress (scope row f4): the same scores, written to `path` column tile by column tile so that the
+ * S x N result never has to fit in host memory (30k sets x 1M cells = 240 GB).  X must be in host
+ * memory; a normalised call makes two passes over X (medians, then scores) exactly like the chunked
+ * plaidgpu_score path, and the bytes written equal what plaidgpu_score returns.
+ *   PLAIDGPU_FILE_RAW: S*N doubles, column-major;  PLAIDGPU_FILE_NPY: NumPy .npy (fortran_order). */
+#define PLAIDGPU_FILE_RAW 0
+#define PLAIDGPU_FILE_NPY 1
+int plaidgpu_score_to_file(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, const int32_t* rowmap,
+                           const plaidgpu_opts* opts, const char* path, int format);
+
 /* t(x) %*% y with x = the gene sets registered by plaidgpu_set_genesets, optionally
  * column-scaled (colscale double[S] or NULL): chunked_crossprod(x, y) (R/plaid.R:100-123).
  * y is X restricted/ordered by rowmap as in plaidgpu_score.  out: S x N dense. */
@@ -265,6 +275,31 @@ void* plaidgpu_stream(const plaidgpu_ctx* ctx);
 int plaidgpu_plan_info(const plaidgpu_ctx* ctx, int32_t* tile_sets, int32_t* n_tiles,
                        int64_t* nnz_mapped, int32_t* warps_per_cta, int32_t* ctas,
                        int32_t* gather_block, int32_t* gather_blocks);
+
+/* ---- expression-matrix files (scope row f4) -------------------------------------------
+ * The on-disk formats on the input side of the path, decoded on the host into the CSC arrays of a
+ * dgCMatrix:
+ *   read_rda : R save() / saveRDS() file (gzip or plain XDR serialisation, version 2 / 3) holding a
+ *              dgCMatrix — the reference's fixture format, inst/extdata/pbmc3k-50cells.rda written by
+ *              dev/extdata.R:15.  `object` = name of the saved object, NULL / "" = the first dgCMatrix.
+ *   read_mtx : Matrix Market coordinate file (real / integer / pattern; general / symmetric), plain
+ *              or .gz; entries in any order, duplicates summed (as(readMM(f), "CsparseMatrix")).
+ *   read_10x : directory with matrix.mtx[.gz], features.tsv[.gz] | genes.tsv[.gz] (rownames = column 2,
+ *              the gene symbols, as Seurat::Read10X(gene.column = 2)) and barcodes.tsv[.gz].
+ * All return PLAIDGPU_OK or PLAIDGPU_ERR_ARG with a message in plaidgpu_io_error() (thread-local). */
+typedef struct plaidgpu_spmat plaidgpu_spmat;
+int plaidgpu_spmat_read_rda(const char* path, const char* object, plaidgpu_spmat** out);
+int plaidgpu_spmat_read_mtx(const char* path, plaidgpu_spmat** out);
+int plaidgpu_spmat_read_10x(const char* dir, plaidgpu_spmat** out);
+void plaidgpu_spmat_free(plaidgpu_spmat* m);
+/* host CSC view of the matrix; the pointers stay valid until plaidgpu_spmat_free */
+int plaidgpu_spmat_view(const plaidgpu_spmat* m, plaidgpu_matrix* M);
+int64_t plaidgpu_spmat_nnz(const plaidgpu_spmat* m);
+int64_t plaidgpu_spmat_num_rownames(const plaidgpu_spmat* m); /* 0 when the file carries no names */
+int64_t plaidgpu_spmat_num_colnames(const plaidgpu_spmat* m);
+const char* plaidgpu_spmat_rowname(const plaidgpu_spmat* m, int64_t k);
+const char* plaidgpu_spmat_colname(const plaidgpu_spmat* m, int64_t k);
+const char* plaidgpu_io_error(void);
 
 #ifdef __cplusplus
 }

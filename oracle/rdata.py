@@ -208,3 +208,113 @@ def dgc_to_scipy(obj: dict):
          np.asarray(obj["p"], dtype=np.int32)), shape=(int(dim[0]), int(dim[1])))
     dn = obj.get("Dimnames") or [None, None]
     return m, dn[0], dn[1]
+
+
+# ---------------------------------------------------------------------------------------
+# writer (tests only): serialise a dgCMatrix the way R's save() / saveRDS() do, so that the product's
+# C++ reader (plaid_b200/csrc/matio.cu) can be exercised on generated files
+# ---------------------------------------------------------------------------------------
+def _w_int(out, v):
+    out.append(struct.pack(">i", v))
+
+
+def _w_sym(out, name, symtab):
+    if name in symtab:  # REFSXP, index packed in the flags
+        _w_int(out, (symtab[name] << 8) | _REFSXP)
+        return
+    symtab[name] = len(symtab) + 1
+    _w_int(out, 1)  # SYMSXP
+    _w_chr(out, name)
+
+
+def _w_chr(out, s):
+    b = s.encode("utf-8")
+    _w_int(out, 9 | (1 << 15))  # CHARSXP, UTF-8 gp bit (0x8000 >> ... R packs levels in bits 12+; value irrelevant to readers)
+    _w_int(out, len(b))
+    out.append(b)
+
+
+def _w_strsxp(out, strings):
+    _w_int(out, 16)
+    _w_int(out, len(strings))
+    for s in strings:
+        _w_chr(out, s)
+
+
+def _w_dgc(out, m, rownames, colnames, symtab):
+    """S4SXP with attribute pairlist i, p, Dim, Dimnames, x, factors, class (slot order of Matrix)"""
+    _w_int(out, 25 | 0x100 | 0x200 | (1 << 16))  # S4SXP, object bit, attributes, S4 gp bit (bit 4 of gp << 12)
+
+    def slot(name, writer):
+        _w_int(out, 2 | 0x400)  # LISTSXP with tag
+        _w_sym(out, name, symtab)
+        writer()
+
+    def ints(v):
+        _w_int(out, 13)
+        _w_int(out, len(v))
+        out.append(np.asarray(v, dtype=">i4").tobytes())
+
+    def reals(v):
+        _w_int(out, 14)
+        _w_int(out, len(v))
+        out.append(np.asarray(v, dtype=">f8").tobytes())
+
+    def dimnames():
+        _w_int(out, 19)
+        _w_int(out, 2)
+        for nm in (rownames, colnames):
+            if nm is None:
+                _w_int(out, _NILVALUE)
+            else:
+                _w_strsxp(out, list(nm))
+
+    def klass():
+        _w_int(out, 16 | 0x200)  # STRSXP with attribute package = "Matrix"
+        _w_int(out, 1)
+        _w_chr(out, "dgCMatrix")
+        _w_int(out, 2 | 0x400)
+        _w_sym(out, "package", symtab)
+        _w_strsxp(out, ["Matrix"])
+        _w_int(out, _NILVALUE)
+
+    slot("i", lambda: ints(m.indices))
+    slot("p", lambda: ints(m.indptr))
+    slot("Dim", lambda: ints(m.shape))
+    slot("Dimnames", dimnames)
+    slot("x", lambda: reals(m.data))
+    slot("factors", lambda: (_w_int(out, 19), _w_int(out, 0)))
+    slot("class", klass)
+    _w_int(out, _NILVALUE)
+
+
+def write_rda(path: str, objects: dict, version: int = 3, compress: bool = True, rds: bool = False):
+    """objects: {name: (scipy csc_matrix, rownames | None, colnames | None)}.  `rds=True` writes the first
+    object the way saveRDS() does (no RDX header, no name)."""
+    out: list = []
+    if not rds:
+        out.append(b"RDX3\n" if version == 3 else b"RDX2\n")
+    out.append(b"X\n")
+    _w_int(out, version)
+    _w_int(out, 0x040303)  # R 4.3.3
+    _w_int(out, 0x030500 if version == 3 else 0x020300)
+    if version == 3:
+        _w_int(out, 5)
+        out.append(b"UTF-8")
+    symtab: dict = {}
+    if rds:
+        m, rn, cn = next(iter(objects.values()))
+        m = m.tocsc()
+        m.sort_indices()
+        _w_dgc(out, m, rn, cn, symtab)
+    else:
+        for name, (m, rn, cn) in objects.items():
+            m = m.tocsc()
+            m.sort_indices()
+            _w_int(out, 2 | 0x400)
+            _w_sym(out, name, symtab)
+            _w_dgc(out, m, rn, cn, symtab)
+        _w_int(out, _NILVALUE)
+    raw = b"".join(out)
+    with open(path, "wb") as fh:
+        fh.write(gzip.compress(raw) if compress else raw)

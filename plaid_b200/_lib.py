@@ -15,6 +15,7 @@ CSC, DENSE = 0, 1
 PLAID, SCSE, SING, SSGSEA, UCELL, AUCELL, GSVA = range(7)
 TIES = {"average": 0, "min": 1, "max": 2}
 ROWTF_Z, ROWTF_ECDF, ROWTF_DONE = 0, 1, 2
+FILE_RAW, FILE_NPY = 0, 1
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOOVERLAP, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
@@ -71,6 +72,18 @@ SYMBOLS = {
     "plaidgpu_gmt_gene_name": (C.c_char_p, [C.c_void_p, C.c_int64]),
     "plaidgpu_gmt_csc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "plaidgpu_gmt_rowmap": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int32, C.c_void_p]),
+    "plaidgpu_score_to_file": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.POINTER(Opts), C.c_char_p, C.c_int]),
+    "plaidgpu_spmat_read_rda": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "plaidgpu_spmat_read_mtx": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "plaidgpu_spmat_read_10x": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "plaidgpu_spmat_free": (None, [C.c_void_p]),
+    "plaidgpu_spmat_view": (C.c_int, [C.c_void_p, C.POINTER(Matrix)]),
+    "plaidgpu_spmat_nnz": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_spmat_num_rownames": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_spmat_num_colnames": (C.c_int64, [C.c_void_p]),
+    "plaidgpu_spmat_rowname": (C.c_char_p, [C.c_void_p, C.c_int64]),
+    "plaidgpu_spmat_colname": (C.c_char_p, [C.c_void_p, C.c_int64]),
+    "plaidgpu_io_error": (C.c_char_p, []),
     "plaidgpu_launch_count": (C.c_int64, [C.c_void_p]),
     "plaidgpu_reset_launch_count": (None, [C.c_void_p]),
     "plaidgpu_last_kernel_ms": (C.c_double, [C.c_void_p, C.c_int]),

@@ -533,3 +533,73 @@ def gmt2mat_file(path: str) -> NamedMatrix:
         return NamedMatrix(G, genes, sets)
     finally:
         lib.plaidgpu_gmt_free(h)
+
+
+# ---------------------------------------------------------------------------------------
+# expression-matrix files and tiled result egress (scope row f4; readers need no GPU)
+# ---------------------------------------------------------------------------------------
+def _spmat_to_named(lib, h) -> NamedMatrix:
+    try:
+        M = L.Matrix()
+        rc = lib.plaidgpu_spmat_view(h, C.byref(M))
+        if rc != L.OK:
+            raise L.PlaidGpuError(rc, "plaidgpu_spmat_view failed")
+        nnz = lib.plaidgpu_spmat_nnz(h)
+        p = np.ctypeslib.as_array(C.cast(M.p, C.POINTER(C.c_int32)), shape=(M.N + 1,)).copy()
+        if nnz:
+            i = np.ctypeslib.as_array(C.cast(M.i, C.POINTER(C.c_int32)), shape=(nnz,)).copy()
+            x = np.ctypeslib.as_array(C.cast(M.x, C.POINTER(C.c_double)), shape=(nnz,)).copy()
+        else:
+            i, x = np.zeros(0, dtype=np.int32), np.zeros(0)
+        rn = [lib.plaidgpu_spmat_rowname(h, k).decode() for k in range(lib.plaidgpu_spmat_num_rownames(h))] or None
+        cn = [lib.plaidgpu_spmat_colname(h, k).decode() for k in range(lib.plaidgpu_spmat_num_colnames(h))] or None
+        return NamedMatrix(sp.csc_matrix((x, i, p), shape=(M.P, M.N)), rn, cn)
+    finally:
+        lib.plaidgpu_spmat_free(h)
+
+
+def _read_spmat(fn_name: str, *args) -> NamedMatrix:
+    lib = L.load()
+    h = C.c_void_p()
+    rc = getattr(lib, fn_name)(*args, C.byref(h))
+    if rc != L.OK:
+        raise L.PlaidGpuError(rc, lib.plaidgpu_io_error().decode(errors="replace"))
+    return _spmat_to_named(lib, h)
+
+
+def read_rda(path: str, name: Optional[str] = None) -> NamedMatrix:
+    """`load(path)` / `readRDS(path)` for a file holding a `dgCMatrix` (the reference's fixture format,
+    inst/extdata/pbmc3k-50cells.rda, dev/extdata.R:15): the sparse matrix with its dimnames."""
+    return _read_spmat("plaidgpu_spmat_read_rda", path.encode(), name.encode() if name else None)
+
+
+def read_mtx(path: str) -> NamedMatrix:
+    """`as(Matrix::readMM(path), "CsparseMatrix")` for Matrix Market coordinate files (plain or .gz)."""
+    return _read_spmat("plaidgpu_spmat_read_mtx", path.encode())
+
+
+def read_10x(directory: str) -> NamedMatrix:
+    """`Seurat::Read10X(directory)`-style ingestion: matrix.mtx[.gz] + features.tsv / genes.tsv (gene symbols as
+    rownames) + barcodes.tsv (colnames).  Names are kept as they are (no make.unique): a duplicated symbol's
+    first row is the one that aligns with matG, like `intersect` + `match` in R/plaid.R:65-72."""
+    return _read_spmat("plaidgpu_spmat_read_10x", directory.encode())
+
+
+def score_to_file(X: NamedMatrix, matG: NamedMatrix, path: str, *, fmt: str = "npy", ctx=None, **opts_kw):
+    """Score and stream the S x N result to `path` in column tiles (results larger than host memory).
+    opts_kw are the plaidgpu_opts fields (default: plaid(), stats = "mean", normalize = TRUE).  Returns (S, N)."""
+    ctx = ctx or default_context()
+    if X.rownames is None or matG.rownames is None:
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    rowmap = make_rowmap(X.rownames, matG.rownames)
+    if not (rowmap >= 0).any():
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    ctx.set_genesets(matG.mat)
+    keep: list = []
+    M = _matrix_struct(X.mat, keep)
+    o = _opts(ctx.lib, **opts_kw)
+    ctx.check(ctx.lib.plaidgpu_score_to_file(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(o), path.encode(),
+                                             L.FILE_NPY if fmt == "npy" else L.FILE_RAW))
+    return int(matG.mat.shape[1]), int(M.N)

@@ -948,8 +948,10 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
 // columns, so a normalised call recomputes the scores: pass 1 keeps only the per-column medians,
 // pass 2 recomputes, fixes up and streams each chunk out (recomputing costs less than moving the raw
 // scores over PCIe twice).  Results are bit-identical to the un-chunked path.
+// `sink` (optional): instead of landing in `out`, every finished chunk is staged in a pinned buffer and
+// written to the file — tiled egress for results larger than host memory (scope row f4).
 static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
-                         double* out, int64_t chunk) {
+                         double* out, int64_t chunk, FILE* sink = nullptr, double* stage = nullptr) {
   const int64_t N = X->N;
   const int32_t S = c->S;
   if (opts->scorer == PLAIDGPU_GSVA && opts->gsva_ecdf != PLAIDGPU_ROWTF_DONE &&
@@ -1021,10 +1023,66 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     if (rc) return rc;
     s.ignore_zero = g.ignore_zero;
     s.med_mean = g.med_mean;
-    rc = plaidgpu_score_finish(c, &s, out + j0 * (int64_t)S);
+    rc = plaidgpu_score_finish(c, &s, sink ? stage : out + j0 * (int64_t)S);
     if (rc) return rc;
+    if (sink) {
+      const size_t cnt = (size_t)(j1 - j0) * (size_t)S;
+      if (fwrite(stage, sizeof(double), cnt, sink) != cnt) return fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
+    }
   }
   return PLAIDGPU_OK;
+}
+
+int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
+                           const char* path, int format) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !opts || !path) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "no gene sets registered");
+  if (X->location != PLAIDGPU_HOST) return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_to_file: X must be in host memory");
+  if (format != PLAIDGPU_FILE_RAW && format != PLAIDGPU_FILE_NPY) return fail(c, PLAIDGPU_ERR_ARG, "unknown file format");
+  CK(cudaSetDevice(c->device));
+  const int32_t S = c->S;
+  const int64_t N = X->N;
+  // column tile: what the device can hold next to X and the ranks, capped at 1 GiB of pinned staging
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  double budget = std::min(0.45 * (double)free_b + (double)c->b_raw.cap, (double)(1ull << 30));
+  if (const char* e = getenv("PLAIDGPU_MAX_OUT_BYTES")) budget = atof(e);  // test knob
+  int64_t chunk = (int64_t)(budget / ((double)S * 8.0));
+  if (chunk < 1) chunk = 1;
+  if (chunk > 32) chunk = (chunk / 32) * 32;
+  if (chunk > N) chunk = std::max<int64_t>(N, 1);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(c, PLAIDGPU_ERR_ARG, std::string("cannot create ") + path);
+  if (format == PLAIDGPU_FILE_NPY) {  // NumPy format 1.0: magic, version, u16 header length, dict, padded to 64
+    std::string dict = "{'descr': '<f8', 'fortran_order': True, 'shape': (" + std::to_string(S) + ", " + std::to_string(N) + "), }";
+    const size_t unpadded = 10 + dict.size() + 1;
+    dict.append((64 - unpadded % 64) % 64, ' ');
+    dict.push_back('\n');
+    const unsigned char head[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(dict.size() & 0xff),
+                                    (unsigned char)(dict.size() >> 8)};
+    fwrite(head, 1, sizeof(head), f);
+    fwrite(dict.data(), 1, dict.size(), f);
+  }
+  double* stage = nullptr;
+  cudaError_t e = cudaMallocHost(&stage, std::max<size_t>((size_t)chunk * (size_t)S * sizeof(double), 8));
+  if (e != cudaSuccess) {
+    fclose(f);
+    return fail_cuda(c, e, "cudaMallocHost (file staging)");
+  }
+  plaidgpu_opts o = *opts;
+  o.out_location = PLAIDGPU_HOST;
+  int rc = PLAIDGPU_OK;
+  if (N <= chunk) {  // one pass: nothing to recompute
+    rc = plaidgpu_score(c, X, rowmap, &o, stage);
+    const size_t cnt = (size_t)N * (size_t)S;
+    if (!rc && cnt && fwrite(stage, sizeof(double), cnt, f) != cnt) rc = fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
+  } else {
+    rc = score_chunked(c, X, rowmap, &o, nullptr, chunk, f, stage);
+  }
+  cudaFreeHost(stage);
+  if (fclose(f) != 0 && !rc) rc = fail(c, PLAIDGPU_ERR_ARG, "closing the output file failed");
+  return rc;
 }
 
 int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,

@@ -448,3 +448,34 @@ def test_properties_linearity_and_column_independence(gpu_ctx):
     z[z == 0] = np.nan
     med = np.nanmedian(z, axis=0)
     assert np.allclose(n, raw - med[None, :] + med.mean(), rtol=0, atol=1e-12)
+
+
+def test_score_to_file_is_bit_identical(tmp_path, monkeypatch):
+    """tiled egress (scope row f4): the result streamed to a .npy / raw file in column tiles equals the
+    in-memory result bit for bit, one tile or many (forced with a small tile budget), normalised or not"""
+    from plaid_b200 import _lib as L
+    P, N, S = 1300, 157, 900
+    X = synth.sparse_x_numpy(P, N, seed=71)
+    G = synth.genesets_numpy(P, S, seed=72, size_cap=(5, 150))
+    names = synth.gene_names(P)
+    Xn, Gn = pb.NamedMatrix(X, names), pb.NamedMatrix(G, names)
+    ctx = pb.Context(0)
+    cases = [(dict(), lambda: pb.plaid(Xn, Gn, ctx=ctx).mat),
+             (dict(normalize=0, stats_mean=0), lambda: pb.plaid(Xn, Gn, stats="sum", normalize=False, ctx=ctx).mat),
+             (dict(scorer=L.UCELL, rmax=120.0), lambda: pb.replaid_ucell(Xn, Gn, rmax=120, ctx=ctx).mat)]
+    whole = [f() for _, f in cases]
+    for budget in (None, S * 8 * 40):  # one tile; 40-column tiles (32 after rounding) -> 5 tiles, ragged tail
+        if budget is not None:
+            monkeypatch.setenv("PLAIDGPU_MAX_OUT_BYTES", str(budget))
+        for (kw, _), ref in zip(cases, whole):
+            path = str(tmp_path / "scores.npy")
+            assert pb.score_to_file(Xn, Gn, path, ctx=ctx, **kw) == (S, N)
+            got = np.load(path, mmap_mode="r")
+            assert got.shape == (S, N) and got.flags.f_contiguous
+            assert np.array_equal(got, ref)
+        raw = str(tmp_path / "scores.bin")
+        pb.score_to_file(Xn, Gn, raw, fmt="raw", ctx=ctx)
+        assert np.array_equal(np.fromfile(raw).reshape((S, N), order="F"), whole[0])
+    monkeypatch.delenv("PLAIDGPU_MAX_OUT_BYTES")
+    with pytest.raises(L.PlaidGpuError, match="cannot create"):
+        pb.score_to_file(Xn, Gn, str(tmp_path / "no_such_dir" / "x.npy"), ctx=ctx)
