@@ -4,14 +4,20 @@ TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only `tests/`, `__graft_entry__.smoke
 and `bench.py`'s CPU-baseline / `--impl reference` legs may import this package.
 The product path (`plaid_b200`, `libplaidgpu.so`) never does.
 
-PARITY UNPINNED: the reference (bigomics/plaid, pure R) cannot be executed in this
-environment (no R, no rpy2) and its own test-suite pins nothing on this path
-(`tests/testthat/test-plaid.R:1-3` asserts 2*2==4).  The oracle is therefore a
-restatement of `R/plaid.R` + the documented semantics of the CRAN/Bioconductor
-routines it calls (Matrix::crossprod, matrixStats::colRanks/colMedians/rowSds,
-sparseMatrixStats::colRanks/rowSds, base::rank), guarded by
-  * dual independent implementations per function (tests/test_oracle.py),
-  * the two usable known answers of the reference vignette
-    (dim(gmt2mat(read.gmt(hallmarks.gmt))) == (4386, 50); dim(plaid(X, matG)) == (50, 50)),
-  * hand-computed miniature cases.
+PARITY: PINNED for the default path, UNPINNED for the rest.
+The reference (bigomics/plaid, pure R) cannot be executed in this environment (no R, no
+rpy2) and its own test-suite pins nothing on this path (`tests/testthat/test-plaid.R:1-3`
+asserts 2*2==4).  What the reference DID publish are the p-values its vignette prints for its
+bundled fixture (doc/plaid-vignette.html: head(plaid.test(X, y, matG, gsetX = plaid(X, matG,
+normalize = TRUE)))), committed as tests/golden/vignette_known_answers.json:
+  * PINNED — read fixture -> gmt2mat -> row alignment -> plaid(mean) -> normalize_medians:
+    the oracle reproduces all 6 printed `p.lm` values (Welch t-test on the rows of gsetX) to
+    the 7 printed digits, which bounds the scores to ~1e-8 relative; and the 6 printed `p.one`
+    values (gene fold changes inside each set) to 1e-6 (tests/test_reference_known_answers.py).
+  * UNPINNED — colranks / sparse_colranks and the replaid.* scorers (sing, ssgsea, scse, ucell,
+    aucell, gsva): no reference output exists for them.  They are restatements of `R/plaid.R` +
+    the documented semantics of the CRAN/Bioconductor routines it calls (Matrix::crossprod,
+    matrixStats::colRanks/colMedians/rowSds, sparseMatrixStats::colRanks/rowSds, base::rank),
+    guarded by dual independent implementations per function (tests/test_oracle.py), the
+    vignette's printed dims ((4386, 50) and (50, 50)) and hand-computed miniature cases.
 """

@@ -1,9 +1,11 @@
 """CPU oracle: numpy/scipy fp64 restatement of the reference's gene-set scoring hot path.
 
-TEST INFRASTRUCTURE — NOT PRODUCT CODE (see oracle/__init__.py).  PARITY UNPINNED: the
-reference is R and cannot run here; every function cites the reference lines it
-restates (paths relative to /root/reference) and is cross-checked by a second
-independent implementation in tests/test_oracle.py.
+TEST INFRASTRUCTURE — NOT PRODUCT CODE (see oracle/__init__.py).  PARITY: plaid() +
+normalize_medians are PINNED by the p-values the reference's vignette prints for its fixture
+(tests/test_reference_known_answers.py); the rank functions and replaid.* scorers are UNPINNED
+(the reference is R, cannot run here, and published no outputs for them).  Every function cites
+the reference lines it restates (paths relative to /root/reference) and is cross-checked by a
+second independent implementation in tests/test_oracle.py.
 
 Matrices travel as `Named(mat, rownames, colnames)` where `mat` is a
 scipy.sparse.csc_matrix (R `dgCMatrix`) or a 2-D numpy array (R base matrix).

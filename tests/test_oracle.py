@@ -1,7 +1,8 @@
 """Oracle self-consistency (CPU): every oracle function against a second, independent
 implementation, the reference vignette's known answers, and hand-computed miniature cases.
-The reference's own tests pin nothing on this path (tests/testthat/test-plaid.R:1-3), so this
-file is what guards the oracle ("parity unpinned", oracle/__init__.py)."""
+The reference's own tests pin nothing on this path (tests/testthat/test-plaid.R:1-3); the p-values its
+vignette prints pin plaid() + normalize_medians (tests/test_reference_known_answers.py), and this file is
+what guards the rest of the oracle ("unpinned", oracle/__init__.py)."""
 import math
 
 import numpy as np
