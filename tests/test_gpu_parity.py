@@ -479,3 +479,76 @@ def test_score_to_file_is_bit_identical(tmp_path, monkeypatch):
     monkeypatch.delenv("PLAIDGPU_MAX_OUT_BYTES")
     with pytest.raises(L.PlaidGpuError, match="cannot create"):
         pb.score_to_file(Xn, Gn, str(tmp_path / "no_such_dir" / "x.npy"), ctx=ctx)
+
+
+def test_full_c4_shard_size_properties():
+    """BASELINE config C4, one GPU's shard (20,000 genes x 125,000 cells x 30,000 sets, 30 GB of scores,
+    inputs generated in HBM like bench.py): the oracle cannot run at this size, so the result is checked through
+    size-independent properties — column independence (bit-exact re-scoring of sampled columns on their own),
+    the degree checksum of every column, exact medians of every column (device sort), and the normalisation
+    identity out = raw - med_j + mean(med)."""
+    import torch
+    from plaid_b200 import _lib as L
+    P, N, S = 20000, 125000, 30000
+    dev = "cuda:0"
+    Gp, Gi = synth.genesets_torch(P, S, seed=synth.SEED0 + 3, device=dev)
+    G = sp.csc_matrix((np.ones(Gi.size), Gi, Gp), shape=(P, S))
+    xp, xi, xx = synth.sparse_x_torch(P, N, seed=synth.SEED0 + 1003, device=dev)
+    names = synth.gene_names(P)
+    Gn = pb.NamedMatrix(G, names)
+    ctx = pb.Context(0)
+    Xd = pb.NamedMatrix(pb.DeviceCSC(xp, xi, xx, (P, N)), names)
+    raw = torch.empty(S * N, dtype=torch.float64, device=dev)
+    out = torch.empty(S * N, dtype=torch.float64, device=dev)
+    assert pb.plaid(Xd, Gn, normalize=False, ctx=ctx, out=raw) is not None
+    assert pb.plaid(Xd, Gn, ctx=ctx, out=out) is not None
+    raw2, out2 = raw.view(N, S), out.view(N, S)  # row j = column j of the S x N column-major result
+
+    # checksum of checksums: sum_s raw[s, j] * n_s == sum_g x[g, j] * degree(g)   (raw is the set MEAN)
+    ns = torch.from_numpy(np.asarray(G.sum(0)).ravel()).to(dev)
+    deg = torch.from_numpy(np.asarray(G.sum(1)).ravel()).to(dev)
+    colid = torch.repeat_interleave(torch.arange(N, device=dev), (xp[1:] - xp[:-1]).long())
+    want = torch.zeros(N, dtype=torch.float64, device=dev).index_add_(0, colid, xx * deg[xi.long()])
+    got = torch.empty(N, dtype=torch.float64, device=dev)
+    for j0 in range(0, N, 8192):
+        got[j0:j0 + 8192] = raw2[j0:j0 + 8192] @ (ns + 1e-8)
+    assert torch.allclose(got, want, rtol=1e-11, atol=0)
+
+    # exact medians of every column (zeros dropped: min(raw) == 0 here), by a device sort
+    assert float(raw.min()) == 0.0
+    med = torch.empty(N, dtype=torch.float64, device=dev)
+    for j0 in range(0, N, 4096):
+        blk = raw2[j0:j0 + 4096]
+        srt = torch.where(blk == 0, torch.full_like(blk, float("inf")), blk).sort(dim=1).values
+        cnt = (blk != 0).sum(dim=1)
+        lo = srt.gather(1, ((cnt - 1) // 2).clamp(min=0)[:, None])[:, 0]
+        hi = srt.gather(1, (cnt // 2).clamp(max=S - 1)[:, None])[:, 0]
+        med[j0:j0 + 4096] = torch.where(cnt > 0, (lo + hi) / 2, torch.zeros_like(lo))
+    c = float(med.mean())
+    worst = 0.0
+    for j0 in range(0, N, 8192):
+        worst = max(worst, float((out2[j0:j0 + 8192] - (raw2[j0:j0 + 8192] - med[j0:j0 + 8192, None] + c)).abs().max()))
+    assert worst < 1e-12  # mean(med): R sums in long double, torch in fp64 pairwise
+
+    # column independence at full size: sampled columns re-scored alone give the same bits
+    rng = np.random.default_rng(5)
+    cols = np.sort(rng.choice(N, size=96, replace=False))
+    p_h = xp.cpu().numpy()
+    parts_i, parts_x, pp = [], [], [0]
+    for j in cols:
+        parts_i.append(xi[p_h[j]:p_h[j + 1]])
+        parts_x.append(xx[p_h[j]:p_h[j + 1]])
+        pp.append(pp[-1] + int(p_h[j + 1] - p_h[j]))
+    sub = pb.NamedMatrix(pb.DeviceCSC(torch.tensor(pp, dtype=torch.int32, device=dev), torch.cat(parts_i), torch.cat(parts_x),
+                                      (P, len(cols))), names)
+    sub_out = torch.empty(S * len(cols), dtype=torch.float64, device=dev)
+    pb.plaid(sub, Gn, normalize=False, ctx=ctx, out=sub_out)
+    assert torch.equal(sub_out.view(len(cols), S), raw2[torch.from_numpy(cols).to(dev)])
+    # the same for a rank scorer (C5-shaped): replaid.sing has no cross-column scalar, so the sampled
+    # columns — ranked and scored alone — must again give the same bits
+    assert pb.replaid_sing(Xd, Gn, ctx=ctx, out=out) is not None
+    pb.replaid_sing(sub, Gn, ctx=ctx, out=sub_out)
+    assert torch.equal(sub_out.view(len(cols), S), out2[torch.from_numpy(cols).to(dev)])
+    assert float(out.min()) >= -0.5 and float(out.max()) <= 0.5  # r / nrow(X) - 0.5
+    del raw, out
+    torch.cuda.empty_cache()
