@@ -10,10 +10,10 @@ replaid.gsva is the exception: its row transform runs ACROS
 needs per-gene sums (all-reduce of P doubles, twice); rowtf "ecdf" needs every gene's values over all
 samples, so the dense shards are re-partitioned column blocks -> row blocks with an all-to-all, ranked
 (plaidgpu_row_ecdf) and sent back — `gsva_shard` below.
-The scalars are exchanged with torch.distributed (NCCL on GPUs, gloo in the CPU tests): all-reduce
-(min / max) of single doubles and an all-gather of the per-column medians, which every rank
-then combines in GLOBAL COLUMN ORDER (plaidgpu_combine_medians), so results are bit-identical
-for any number of shards.
+The scalars are exchanged with torch.distributed (NCCL on GPUs, gloo in the CPU tests): one
+all-reduce(max) of (-x_min, x_max, rank_max), one all-reduce(min) of the score minimum and one
+all-gather of both per-column median vectors, which every rank then combines in GLOBAL COLUMN
+ORDER (plaidgpu_combine_medians), so results are bit-identical for any number of shards.
 """
 from __future__ import annotations
 
@@ -35,8 +35,14 @@ class LocalComm:
     def allreduce_max(self, v: float) -> float:
         return v
 
+    def allreduce_max_vec(self, v: np.ndarray) -> np.ndarray:
+        return v
+
     def allgather_vec(self, v: np.ndarray) -> np.ndarray:
         return v
+
+    def allgather_vecs(self, vs):
+        return list(vs)
 
     def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
         return v
@@ -73,8 +79,14 @@ class ThreadComm:
     def allreduce_max(self, v: float) -> float:
         return max(self._exchange(v))
 
+    def allreduce_max_vec(self, v: np.ndarray) -> np.ndarray:
+        return np.max(np.stack(self._exchange(np.asarray(v, dtype=np.float64))), axis=0)
+
     def allgather_vec(self, v: np.ndarray) -> np.ndarray:
         return np.concatenate(self._exchange(np.asarray(v, dtype=np.float64)))
+
+    def allgather_vecs(self, vs):
+        return [self.allgather_vec(v) for v in vs]
 
     def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
         vals = self._exchange(np.asarray(v, dtype=np.float64))
@@ -111,20 +123,32 @@ class TorchComm:
     def allreduce_max(self, v: float) -> float:
         return self._red(v, self.dist.ReduceOp.MAX)
 
+    def allreduce_max_vec(self, v: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy()
+
+    def allgather_vecs(self, vs):
+        """several float64 vectors of one common (per-rank) length: ONE size exchange, ONE all-gather of the
+        stacked vectors and ONE copy back; returns the list of rank-order concatenations"""
+        torch, dist = self.torch, self.dist
+        k, n = len(vs), int(vs[0].size)
+        sz = torch.tensor([n], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(sz) for _ in range(self.world)]
+        dist.all_gather(sizes, sz, group=self.group)
+        sizes = [int(t.item()) for t in sizes]
+        m = max(max(sizes), 1)
+        buf = torch.zeros((k, m), dtype=torch.float64, device=self.device)
+        if n:
+            buf[:, :n] = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float64) for v in vs]))).to(self.device)
+        out = torch.empty((self.world, k, m), dtype=torch.float64, device=self.device)
+        dist.all_gather([out[r] for r in range(self.world)], buf, group=self.group)
+        host = out.cpu().numpy()
+        return [np.concatenate([host[r, i, :sizes[r]] for r in range(self.world)]) for i in range(k)]
+
     def allgather_vec(self, v: np.ndarray) -> np.ndarray:
         """concatenate variable-length float64 vectors of all ranks in rank order"""
-        torch, dist = self.torch, self.dist
-        n = torch.tensor([v.size], dtype=torch.int64, device=self.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(sizes) if sizes else 0
-        buf = torch.zeros(max(m, 1), dtype=torch.float64, device=self.device)
-        if v.size:
-            buf[:v.size] = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
-        parts = [torch.empty_like(buf) for _ in range(self.world)]
-        dist.all_gather(parts, buf, group=self.group)
-        return np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)]) if sizes else v
+        return self.allgather_vecs([np.asarray(v, dtype=np.float64)])[0]
 
     def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
         """element-wise sum over ranks, added in RANK ORDER on every rank (not a tree all-reduce), so
@@ -166,17 +190,16 @@ def combine_scalars(comm, local: L.Scalars) -> L.Scalars:
     """step 2 of the protocol in include/plaidgpu.h: x_min (min), x_max (max), rank_max (max)."""
     g = L.Scalars()
     C.memmove(C.byref(g), C.byref(local), C.sizeof(L.Scalars))
-    g.x_min = comm.allreduce_min(local.x_min)
-    g.x_max = comm.allreduce_max(local.x_max)
-    g.rank_max = comm.allreduce_max(local.rank_max)
+    # one all-reduce(max) of (-x_min, x_max, rank_max): min(a) == -max(-a), exact in fp64
+    r = comm.allreduce_max_vec(np.array([-local.x_min, local.x_max, local.rank_max], dtype=np.float64))
+    g.x_min, g.x_max, g.rank_max = -float(r[0]), float(r[1]), float(r[2])
     return g
 
 
 def combine_medians(lib, comm, ignore_zero_opt: int, scal: L.Scalars, med_all: np.ndarray, med_nz: np.ndarray):
     """step 4: global score_min, all medians in column order -> ignore_zero flag + mean(medx)."""
     smin = comm.allreduce_min(scal.score_min)
-    ga = np.ascontiguousarray(comm.allgather_vec(med_all), dtype=np.float64)
-    gz = np.ascontiguousarray(comm.allgather_vec(med_nz), dtype=np.float64)
+    ga, gz = (np.ascontiguousarray(v, dtype=np.float64) for v in comm.allgather_vecs([med_all, med_nz]))
     rc = lib.plaidgpu_combine_medians(int(ignore_zero_opt), smin, ga.ctypes.data, gz.ctypes.data, ga.size, C.byref(scal))
     if rc != L.OK:
         raise L.PlaidGpuError(rc, "plaidgpu_combine_medians failed")
