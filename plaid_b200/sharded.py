@@ -111,6 +111,7 @@ class TorchComm:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.device = device if device is not None else "cpu"
+        self._pin = {}
 
     def _red(self, v: float, op):
         t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
@@ -143,7 +144,16 @@ class TorchComm:
             buf[:, :n] = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float64) for v in vs]))).to(self.device)
         out = torch.empty((self.world, k, m), dtype=torch.float64, device=self.device)
         dist.all_gather([out[r] for r in range(self.world)], buf, group=self.group)
-        host = out.cpu().numpy()
+        if out.is_cuda:  # pinned staging (cached): a pageable 16 MB copy costs ~3 ms per step at 8 ranks
+            key = tuple(out.shape)
+            pin = self._pin.get(key)
+            if pin is None:
+                pin = self._pin[key] = torch.empty(key, dtype=torch.float64, pin_memory=True)
+            pin.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(out.device).synchronize()
+            host = pin.numpy()
+        else:
+            host = out.numpy()
         return [np.concatenate([host[r, i, :sizes[r]] for r in range(self.world)]) for i in range(k)]
 
     def allgather_vec(self, v: np.ndarray) -> np.ndarray:
