@@ -173,6 +173,14 @@ int plaidgpu_score_compute(plaidgpu_ctx* ctx, plaidgpu_scalars* scal, double* ou
 /* per-column medians of the raw scores of this shard: med_all (NaN dropped) and med_nz
  * (NaN and zeros dropped, all-dropped -> 0); each double[N_shard] (host). */
 int plaidgpu_get_col_medians(plaidgpu_ctx* ctx, double* med_all, double* med_nz);
+/* The one median vector normalize_medians will use once the global flag is known: ignore_zero != 0 ->
+ * medians over the non-zero scores, else over all scores; med: host double[N of this shard].  The library
+ * computes up front only the median its own shard's minimum predicts (min > 0: no zeros, both coincide;
+ * min < 0: plain; min == 0: non-zero) and computes the other one here on demand — which only happens when
+ * this shard's minimum is 0 and another shard holds a negative score.  plaidgpu_get_col_medians (both
+ * vectors) stays available and fills in whatever is missing the same way.  Call before *_finish. */
+int plaidgpu_get_col_medians_for(plaidgpu_ctx* ctx, int ignore_zero, double* med);
+
 /* ignore_zero_opt: -1 auto from score_min; med_* over ALL columns of ALL shards in order.
  * Writes scal->ignore_zero and scal->med_mean (= R mean(medx, na.rm=TRUE)). */
 int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double* med_all,

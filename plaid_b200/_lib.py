@@ -54,6 +54,7 @@ SYMBOLS = {
     "plaidgpu_score_begin": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.POINTER(Opts), C.POINTER(Scalars)]),
     "plaidgpu_score_compute": (C.c_int, [C.c_void_p, C.POINTER(Scalars), C.c_void_p]),
     "plaidgpu_get_col_medians": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plaidgpu_get_col_medians_for": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "plaidgpu_combine_medians": (C.c_int, [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Scalars)]),
     "plaidgpu_score_finish": (C.c_int, [C.c_void_p, C.POINTER(Scalars), C.c_void_p]),
     "plaidgpu_crossprod": (C.c_int, [C.c_void_p, C.POINTER(Matrix), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -84,6 +84,11 @@ struct plaidgpu_ctx {
   DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb, b_fail, b_list, b_ci, b_cx, b_ce;
   double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
   bool need_norm = false;
+  // which column medians of the raw scores are known (the statistics pass computes only the one the
+  // shard's own minimum says normalize_medians will use; the other is computed on demand)
+  bool have_all = false, have_nz = false, raw_valid = false, want_both = false;
+  double local_min = INFINITY;
+  DevBuf b_smin;
   std::vector<double> h_med_all, h_med_nz, h_colmin;
   const double* score_vals = nullptr;  // what the score kernel reads as values
   const double* score_r0 = nullptr;
@@ -400,6 +405,54 @@ int row_moments(plaidgpu_ctx* c, const double* mean_host, double* out_host) {
 
 bool is_rank_scorer(int s) {
   return s == PLAIDGPU_SING || s == PLAIDGPU_SSGSEA || s == PLAIDGPU_UCELL || s == PLAIDGPU_AUCELL;
+}
+
+// order-preserving key -> double on the host (inverse of key_of in common.cuh)
+double host_value_of(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  double d;
+  memcpy(&d, &b, sizeof(d));
+  return d;
+}
+
+// the statistics pass over the raw scores of the current call
+int run_colstats(plaidgpu_ctx* c, int which) {
+  CK(c->b_med_all.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+  CK(c->b_med_nz.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+  CK(c->b_colmin.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
+  CK(c->b_fail.reserve(sizeof(int)));
+  CK(c->b_list.reserve(std::max<int64_t>(c->N, 1) * sizeof(int64_t)));
+  CK(launch_colstats(c->raw, c->S, c->S, c->N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(),
+                     c->b_colmin.as<double>(), c->b_fail.as<int>(), c->b_list.as<int64_t>(), which, c->stream));
+  c->launches += 1;
+  if (which != COLSTATS_NZ) c->have_all = true;
+  if (which != COLSTATS_ALL) c->have_nz = true;
+  return PLAIDGPU_OK;
+}
+
+int fetch_medians(plaidgpu_ctx* c) {
+  c->h_med_all.resize((size_t)c->N);
+  c->h_med_nz.resize((size_t)c->N);
+  c->h_colmin.resize((size_t)c->N);
+  if (c->N) {
+    if (c->have_all)
+      CK(cudaMemcpyAsync(c->h_med_all.data(), c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->have_nz)
+      CK(cudaMemcpyAsync(c->h_med_nz.data(), c->b_med_nz.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_colmin.data(), c->b_colmin.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return PLAIDGPU_OK;
+}
+
+// make the plain (want_nz = false) or the non-zero median of every column available on device and host
+int ensure_median(plaidgpu_ctx* c, bool want_nz) {
+  if (want_nz ? c->have_nz : c->have_all) return PLAIDGPU_OK;
+  if (!c->raw_valid) return fail(c, PLAIDGPU_ERR_STATE, "the raw scores are gone (plaidgpu_score_finish already ran)");
+  CK(cudaSetDevice(c->device));
+  int rc = run_colstats(c, want_nz ? COLSTATS_NZ : COLSTATS_ALL);
+  if (rc) return rc;
+  return fetch_medians(c);
 }
 
 int max_col_nnz(plaidgpu_ctx* c, int32_t* out) {
@@ -774,9 +827,17 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     p.colscale = c->d_colscale.as<double>();
   }
 
+  unsigned long long* smin = nullptr;
+  if (c->need_norm) {  // the score kernels report their smallest final score (see ensure_median)
+    CK(c->b_smin.reserve(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->b_smin.p, 0xFF, sizeof(unsigned long long), c->stream));
+    smin = c->b_smin.as<unsigned long long>();
+  }
+  p.smin = smin;
   CK(cudaEventRecord(c->ev[0], c->stream));
   if (c->gblocks > 0) {
     GatherParams g{};
+    g.smin = smin;
     g.xp = c->xp;
     g.xi = c->xi;
     g.xx = p.xx;
@@ -825,25 +886,32 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   CK(cudaEventRecord(c->ev[1], c->stream));
 
   scal->score_min = INFINITY;
+  c->have_all = c->have_nz = false;
+  c->raw_valid = true;
   if (c->need_norm) {
-    CK(c->b_med_all.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
-    CK(c->b_med_nz.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
-    CK(c->b_colmin.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
-    CK(cudaEventRecord(c->ev[2], c->stream));
-    CK(c->b_fail.reserve(sizeof(int)));
-    CK(c->b_list.reserve(std::max<int64_t>(c->N, 1) * sizeof(int64_t)));
-    CK(launch_colstats(c->raw, c->S, c->S, c->N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(),
-                       c->b_colmin.as<double>(), c->b_fail.as<int>(), c->b_list.as<int64_t>(), c->stream));
-    c->launches += 1;
-    CK(cudaEventRecord(c->ev[3], c->stream));
-    c->h_med_all.resize((size_t)c->N);
-    c->h_med_nz.resize((size_t)c->N);
-    c->h_colmin.resize((size_t)c->N);
-    if (c->N) {
-      CK(cudaMemcpyAsync(c->h_med_all.data(), c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(c->h_med_nz.data(), c->b_med_nz.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(c->h_colmin.data(), c->b_colmin.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // normalize_medians uses ONE of the two medians, chosen by min(x) == 0 over all shards (R/plaid.R:556-557).
+    // The shard's own minimum (tracked by the score kernels) settles which: > 0 -> no zeros here, both medians
+    // coincide; < 0 -> the global minimum is negative too, the plain median is used; == 0 -> the non-zero
+    // median, unless another shard holds a negative score (then the plain one is computed on demand).
+    unsigned long long key = ~0ull;
+    CK(cudaMemcpyAsync(&key, c->b_smin.p, sizeof(key), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->local_min = (key == ~0ull) ? INFINITY : host_value_of(key);
+    int which = COLSTATS_BOTH;
+    if (!c->want_both && !colstats_small(c->S)) {
+      if (o.ignore_zero >= 0) which = o.ignore_zero ? COLSTATS_NZ : COLSTATS_ALL;
+      else which = (c->local_min == 0.0) ? COLSTATS_NZ : COLSTATS_ALL;
     }
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    int rc = run_colstats(c, which);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    if (which == COLSTATS_ALL && c->local_min > 0.0 && c->N) {  // no zeros: the two medians are the same numbers
+      CK(cudaMemcpyAsync(c->b_med_nz.p, c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      c->have_nz = true;
+    }
+    rc = fetch_medians(c);
+    if (rc) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
@@ -863,9 +931,23 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
 int plaidgpu_get_col_medians(plaidgpu_ctx* c, double* med_all, double* med_nz) {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!c->computed || !c->need_norm) return fail(c, PLAIDGPU_ERR_STATE, "no medians: run plaidgpu_score_compute with normalisation");
-  if (med_all) memcpy(med_all, c->h_med_all.data(), (size_t)c->N * sizeof(double));
-  if (med_nz) memcpy(med_nz, c->h_med_nz.data(), (size_t)c->N * sizeof(double));
+  if (med_all) {
+    int rc = ensure_median(c, false);
+    if (rc) return rc;
+    memcpy(med_all, c->h_med_all.data(), (size_t)c->N * sizeof(double));
+  }
+  if (med_nz) {
+    int rc = ensure_median(c, true);
+    if (rc) return rc;
+    memcpy(med_nz, c->h_med_nz.data(), (size_t)c->N * sizeof(double));
+  }
   return PLAIDGPU_OK;
+}
+
+int plaidgpu_get_col_medians_for(plaidgpu_ctx* c, int ignore_zero, double* med) {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!med && c->N > 0) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  return ignore_zero ? plaidgpu_get_col_medians(c, nullptr, med) : plaidgpu_get_col_medians(c, med, nullptr);
 }
 
 int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double* med_all, const double* med_nz,
@@ -892,6 +974,8 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
   const double* beta = nullptr;
   bool fix = false;
   if (c->need_norm) {
+    int rc = ensure_median(c, scal->ignore_zero != 0);
+    if (rc) return rc;
     med = scal->ignore_zero ? c->b_med_nz.as<double>() : c->b_med_all.as<double>();
     cc = scal->med_mean;
     fix = true;
@@ -908,6 +992,7 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
     fix = true;
   }
 
+  c->raw_valid = false;  // the fix-up below rewrites the raw scores in place
   CK(cudaEventRecord(c->ev[4], c->stream));
   if (o.out_location == PLAIDGPU_DEVICE) {
     if (out != c->raw) return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_finish: device `out` differs from the buffer given to compute");
@@ -998,6 +1083,12 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   if (norm) {
     std::vector<double> ma((size_t)N), mz((size_t)N);
     double smin = INFINITY;
+    // the raw scores of a chunk are gone when the global min(x) == 0 flag is known: keep both medians
+    struct BothGuard {
+      plaidgpu_ctx* c;
+      ~BothGuard() { c->want_both = false; }
+    } guard{c};
+    c->want_both = opts->ignore_zero < 0;
     for (int64_t j0 = 0; j0 < N; j0 += chunk) {
       const int64_t j1 = std::min(N, j0 + chunk);
       sub(j0, j1, &M);
@@ -1013,10 +1104,12 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     rc = plaidgpu_combine_medians(opts->ignore_zero, smin, ma.data(), mz.data(), N, &g);
     if (rc) return fail(c, rc, "combine_medians failed");
   }
+  plaidgpu_opts o2 = *opts;
+  if (norm) o2.ignore_zero = g.ignore_zero;  // decided: the second pass needs only that median
   for (int64_t j0 = 0; j0 < N; j0 += chunk) {
     const int64_t j1 = std::min(N, j0 + chunk);
     sub(j0, j1, &M);
-    rc = plaidgpu_score_begin(c, &M, rowmap, opts, &loc);
+    rc = plaidgpu_score_begin(c, &M, rowmap, &o2, &loc);
     if (rc) return rc;
     plaidgpu_scalars s = g;
     rc = plaidgpu_score_compute(c, &s, nullptr);
@@ -1110,7 +1203,12 @@ int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* row
   rc = plaidgpu_score_compute(c, &s, out);
   if (rc) return rc;
   if (c->need_norm) {
-    rc = plaidgpu_combine_medians(opts->ignore_zero, s.score_min, c->h_med_all.data(), c->h_med_nz.data(), c->N, &s);
+    // one shard holds every column: its own minimum decides, and only that median was computed
+    const bool iz = opts->ignore_zero < 0 ? (s.score_min == 0.0) : (opts->ignore_zero != 0);
+    rc = ensure_median(c, iz);
+    if (rc) return rc;
+    const double* m = iz ? c->h_med_nz.data() : c->h_med_all.data();
+    rc = plaidgpu_combine_medians(opts->ignore_zero, s.score_min, m, m, c->N, &s);
     if (rc) return fail(c, rc, "combine_medians failed");
   }
   return plaidgpu_score_finish(c, &s, out);
@@ -1295,8 +1393,10 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int6
   CK(cudaEventRecord(c->ev[2], c->stream));
   CK(c->b_fail.reserve(sizeof(int)));
   CK(c->b_list.reserve(std::max<int64_t>(N, 1) * sizeof(int64_t)));
+  // ignore.zero given: one median; auto: the flag needs min(x) first, so both come out of the same pass
+  const int which = ignore_zero < 0 ? COLSTATS_BOTH : (ignore_zero ? COLSTATS_NZ : COLSTATS_ALL);
   CK(launch_colstats(dx, S, S, N, c->b_med_all.as<double>(), c->b_med_nz.as<double>(), c->b_colmin.as<double>(),
-                     c->b_fail.as<int>(), c->b_list.as<int64_t>(), c->stream));
+                     c->b_fail.as<int>(), c->b_list.as<int64_t>(), which, c->stream));
   c->launches += 1;
   CK(cudaEventRecord(c->ev[3], c->stream));
   c->h_med_all.resize((size_t)N);

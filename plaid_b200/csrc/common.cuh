@@ -53,6 +53,9 @@ struct ScoreParams {
   // output, column-major S x N, leading dimension ld
   double* out;
   int64_t ld;
+  // optional: order-preserving key (key_of) of the smallest FINAL score written, atomicMin'ed per warp;
+  // tells the host which median normalize_medians will need before the statistics pass runs
+  unsigned long long* smin;
 };
 
 // Gather pass over one block of K genes (the dense-ish part of the product):
@@ -82,6 +85,7 @@ struct GatherParams {
   int32_t nsplit;        // CTAs per column batch (set range split), set by launch_gather
   double* out;
   int64_t ld;
+  unsigned long long* smin;  // as in ScoreParams
 };
 
 struct LaunchCfg {
@@ -110,8 +114,13 @@ cudaError_t launch_colabs(const int32_t* xp, const double* xx, int32_t P, int64_
 //   med_nz[j] : median over non-NaN, non-zero values (0 when none)        (R/plaid.R:561-566)
 //   colmin[j] : min over non-NaN values (+inf when none)
 // d_fail: 1 int, d_list: N int64 of device scratch (columns the single-pass kernel hands to the exact one)
+// which: COLSTATS_BOTH, or only one of the medians when the caller already knows which one
+// normalize_medians will use (the other array is then left untouched, except for columns that fall back
+// to the exact kernel, which always writes both)
+enum { COLSTATS_BOTH = 0, COLSTATS_ALL = 1, COLSTATS_NZ = 2 };
+bool colstats_small(int32_t S);  // short columns go to the exact kernel, which always yields both medians
 cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
-                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, cudaStream_t st);
+                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, int which, cudaStream_t st);
 // out[s,j] = alpha * (x[s,j] - med[j] + c) + (beta ? beta[s] : 0); med may be nullptr (then 0)
 cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, int64_t j0, int64_t j1,
                          const double* med, double c, double alpha, const double* beta,

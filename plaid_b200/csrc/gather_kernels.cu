@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   double* __restrict__ stw = st + (size_t)w * GC * GPAD;
   const int K = p.K;
+  double vmin = INFINITY;  // smallest final score this thread wrote (p.smin)
   const int64_t nbatch = (p.N + GC - 1) / GC;
   // few columns (bulk data): several CTAs share one batch and split the set range between them
   const int nsplit = p.nsplit, split = blockIdx.x % nsplit;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
             double fb = 0.0;
             if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
             v = score_epilogue(v, s, j, fb, p.mode, p.inv, p.ns, p.colscale);
+            vmin = fmin(vmin, v);
           }
           __stcs(o, v);
         }
@@ -130,6 +132,15 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
       __syncwarp();
     }
     __syncthreads();  // Xs is rebuilt by the next batch
+  }
+  if (p.final && p.smin) {  // smallest final score of this warp -> one atomicMin
+    unsigned long long k = vmin == INFINITY ? ~0ull : key_of(vmin);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(FULL, k, o);
+      k = other < k ? other : k;
+    }
+    if (lane == 0 && k != ~0ull) atomicMin(p.smin, k);
   }
 }
 

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(768, 1) k_scatter(const ScoreParams p) {
   for (int l = lane; l < p.Ts; l += 32) acc[l] = 0.0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
+  double vmin = INFINITY;  // smallest final score this thread wrote (p.smin)
 
   const int T = p.T;
   const int64_t ncols_cta = (p.N - blockIdx.x + gridDim.x - 1) / gridDim.x;  // columns of this CTA
@@ -223,12 +224,22 @@ __global__ void __launch_bounds__(768, 1) k_scatter(const ScoreParams p) {
           if (p.final) {
             if (rankmode) v += fb * nv[u];
             v = v * iv[u] * csj;
+            vmin = fmin(vmin, v);
           }
           __stcs(o + l, v);
         }
       }
     }
     __syncwarp();
+  }
+  if (p.final && p.smin) {  // smallest final score of this warp -> one atomicMin
+    unsigned long long k = vmin == INFINITY ? ~0ull : key_of(vmin);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(FULL, k, o);
+      k = other < k ? other : k;
+    }
+    if (lane == 0 && k != ~0ull) atomicMin(p.smin, k);
   }
 }
 

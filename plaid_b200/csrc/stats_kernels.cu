@@ -436,6 +436,9 @@ __device__ void select_from_list(Stats2Smem& s, const unsigned long long* list, 
   }
 }
 
+// DO0 / DO1: which medians are wanted (all valid values / the non-zero values).  The caller usually knows
+// which one normalize_medians will use (R/plaid.R:556-557) before this pass; the unused bracket is compiled out.
+template <bool DO0, bool DO1>
 __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__ x, int64_t ld, int32_t S, int64_t N,
                                                       double* __restrict__ med_all, double* __restrict__ med_nz,
                                                       double* __restrict__ colmin, int* __restrict__ fail_count,
@@ -479,6 +482,10 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
       }
       // bracket g = 0: median of all valid values; g = 1: median of the non-zero values
       for (int g = 0; g < 2; ++g) {
+        if (!(g == 0 ? DO0 : DO1)) {
+          s.lo[g] = s.hi[g] = 0ull;
+          continue;
+        }
         const int mcount = g == 0 ? mv : mv - (ze - zs);
         if (mcount < 48) {  // too few sample points: take everything (the candidate cap decides)
           s.lo[g] = key_of(-INFINITY);
@@ -533,12 +540,12 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
         nnan += isnan_;
         nzero += isz;
         minv = fmin(minv, v);
-        const bool lt0 = f < lo0f, gt0 = f > hi0f;
-        const bool lt1 = f < lo1f, gt1 = f > hi1f;
-        bel0 += lt0;
-        bel1 += lt1 && !isz;
-        const bool mid0 = !(lt0 || gt0 || isnan_);
-        const bool mid1 = !(lt1 || gt1 || isnan_ || isz);
+        const bool lt0 = DO0 && f < lo0f, gt0 = DO0 && f > hi0f;
+        const bool lt1 = DO1 && f < lo1f, gt1 = DO1 && f > hi1f;
+        if (DO0) bel0 += lt0;
+        if (DO1) bel1 += lt1 && !isz;
+        const bool mid0 = DO0 && !(lt0 || gt0 || isnan_);
+        const bool mid1 = DO1 && !(lt1 || gt1 || isnan_ || isz);
         const unsigned mm = __ballot_sync(FULL, mid0 || mid1);
         if (mm) {
           // exact tests for the undecided rows; every warp appends to its own segment (no atomics)
@@ -600,6 +607,7 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
     const unsigned cnt[2] = {nvalid, nvalid - s.nzero};
     bool good = true;
     for (int g = 0; g < 2; ++g) {
+      if (!(g == 0 ? DO0 : DO1)) continue;
       if (cnt[g] == 0) continue;
       const unsigned ka = (cnt[g] - 1) / 2, kb = cnt[g] / 2;
       const unsigned b = s.below[g], e1 = b + s.eqlo[g], nin = s.ncand[g], e2 = e1 + nin, e3 = e2 + s.eqhi[g];
@@ -630,16 +638,16 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
         fail_list[slot] = j;
       } else {
         double ma = nan(""), mz = 0.0;
-        if (cnt[0] > 0) {
+        if (DO0 && cnt[0] > 0) {
           const double a = value_of(s.res[0][0]), b = value_of(s.res[0][1]);
           ma = (cnt[0] & 1u) ? a : (a + b) / 2.0;
         }
-        if (cnt[1] > 0) {
+        if (DO1 && cnt[1] > 0) {
           const double a = value_of(s.res[1][0]), b = value_of(s.res[1][1]);
           mz = (cnt[1] & 1u) ? a : (a + b) / 2.0;
         }
-        med_all[j] = ma;
-        med_nz[j] = mz;
+        if (DO0) med_all[j] = ma;
+        if (DO1) med_nz[j] = mz;
         colmin[j] = nvalid > 0 ? value_of(s.minkey) : INFINITY;
       }
     }
@@ -756,15 +764,21 @@ __global__ void k_minmax_fin(const unsigned long long* res, double* out) {
 
 }  // namespace
 
+bool colstats_small(int32_t S) { return S < 4 * SAMP; }
+
 cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, double* med_all,
-                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, cudaStream_t st) {
+                            double* med_nz, double* colmin, int* d_fail, int64_t* d_list, int which, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
   {  // per device (a process may drive several GPUs): cheap, so set on every launch
     cudaError_t e = cudaFuncSetAttribute(k_colstats, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(StatsSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_colstats_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats2Smem));
-    if (e != cudaSuccess) return e;
+    const void* fast[3] = {(const void*)k_colstats_fast<true, true>, (const void*)k_colstats_fast<true, false>,
+                           (const void*)k_colstats_fast<false, true>};
+    for (const void* f : fast) {
+      e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats2Smem));
+      if (e != cudaSuccess) return e;
+    }
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -780,11 +794,21 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
   cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast, NT, sizeof(Stats2Smem));
+  if (which == COLSTATS_ALL)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, false>, NT, sizeof(Stats2Smem));
+  else if (which == COLSTATS_NZ)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<false, true>, NT, sizeof(Stats2Smem));
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, true>, NT, sizeof(Stats2Smem));
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > N) grid = N;
-  k_colstats_fast<<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+  if (which == COLSTATS_ALL)
+    k_colstats_fast<true, false><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+  else if (which == COLSTATS_NZ)
+    k_colstats_fast<false, true><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+  else
+    k_colstats_fast<true, true><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   int nfail = 0;

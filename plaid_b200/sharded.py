@@ -216,6 +216,22 @@ def combine_medians(lib, comm, ignore_zero_opt: int, scal: L.Scalars, med_all: n
     return scal
 
 
+def combine_medians_of(ctx, comm, ignore_zero_opt: int, scal: L.Scalars, n_cols: int):
+    """step 4 for a live context: the global score minimum settles ignore.zero first, so only THAT median vector
+    is fetched (plaidgpu_get_col_medians_for: already computed unless this shard's minimum is 0 while another
+    shard holds a negative score) and all-gathered; every rank then takes mean(medx) in global column order."""
+    lib = ctx.lib
+    smin = comm.allreduce_min(scal.score_min)
+    iz = (smin == 0.0) if ignore_zero_opt < 0 else bool(ignore_zero_opt)
+    med = np.empty(max(n_cols, 0), dtype=np.float64)
+    ctx.check(lib.plaidgpu_get_col_medians_for(ctx.h, int(iz), med.ctypes.data))
+    g = np.ascontiguousarray(comm.allgather_vec(med), dtype=np.float64)
+    rc = lib.plaidgpu_combine_medians(int(ignore_zero_opt), smin, g.ctypes.data, g.ctypes.data, g.size, C.byref(scal))
+    if rc != L.OK:
+        raise L.PlaidGpuError(rc, "plaidgpu_combine_medians failed")
+    return scal
+
+
 def score_shard(ctx, comm, M: L.Matrix, rowmap: np.ndarray, opts: L.Opts, out_ptr: int, n_cols: int):
     """Run the begin / compute / finish protocol for this rank's column shard."""
     lib = ctx.lib
@@ -225,10 +241,7 @@ def score_shard(ctx, comm, M: L.Matrix, rowmap: np.ndarray, opts: L.Opts, out_pt
     ctx.check(lib.plaidgpu_score_compute(ctx.h, C.byref(scal), out_ptr))
     needs_norm = (opts.scorer in (L.SSGSEA, L.UCELL, L.AUCELL, L.GSVA)) or (opts.scorer == L.PLAID and opts.normalize)
     if needs_norm:
-        ma = np.empty(n_cols, dtype=np.float64)
-        mz = np.empty(n_cols, dtype=np.float64)
-        ctx.check(lib.plaidgpu_get_col_medians(ctx.h, ma.ctypes.data, mz.ctypes.data))
-        combine_medians(lib, comm, opts.ignore_zero, scal, ma, mz)
+        combine_medians_of(ctx, comm, opts.ignore_zero, scal, n_cols)
     ctx.check(lib.plaidgpu_score_finish(ctx.h, C.byref(scal), out_ptr))
     return scal
 
@@ -322,17 +335,16 @@ def score_multi(ctxs, mats, rowmap: np.ndarray, opts_list, out_ptrs, n_cols):
         scal.append(s)
     o0 = opts_list[0]
     if (o0.scorer in (L.SSGSEA, L.UCELL, L.AUCELL, L.GSVA)) or (o0.scorer == L.PLAID and o0.normalize):
-        mas, mzs = [], []
-        for c, n in zip(ctxs, n_cols):
-            ma = np.empty(n)
-            mz = np.empty(n)
-            c.check(lib.plaidgpu_get_col_medians(c.h, ma.ctypes.data, mz.ctypes.data))
-            mas.append(ma)
-            mzs.append(mz)
-        ga, gz = np.concatenate(mas), np.concatenate(mzs)
         smin = min(s.score_min for s in scal)
+        iz = (smin == 0.0) if o0.ignore_zero < 0 else bool(o0.ignore_zero)
+        meds = []
+        for c, n in zip(ctxs, n_cols):
+            m = np.empty(n)
+            c.check(lib.plaidgpu_get_col_medians_for(c.h, int(iz), m.ctypes.data))
+            meds.append(m)
+        g = np.ascontiguousarray(np.concatenate(meds))
         for s in scal:
-            rc = lib.plaidgpu_combine_medians(int(o0.ignore_zero), smin, ga.ctypes.data, gz.ctypes.data, ga.size, C.byref(s))
+            rc = lib.plaidgpu_combine_medians(int(o0.ignore_zero), smin, g.ctypes.data, g.ctypes.data, g.size, C.byref(s))
             if rc != L.OK:
                 raise L.PlaidGpuError(rc, "plaidgpu_combine_medians failed")
     for c, s, outp in zip(ctxs, scal, out_ptrs):

@@ -343,6 +343,60 @@ def test_sharded_protocol_is_shard_count_invariant():
             assert np.array_equal(np.concatenate(outs, axis=1), whole)
 
 
+def test_median_choice_across_shards():
+    """normalize_medians uses ONE median, picked by min(x) == 0 over ALL shards (R/plaid.R:556-557); each shard
+    computes up front only the median its own minimum predicts and the other one on demand.  Long columns
+    (S >= 4096: the single-pass statistics kernel) in every constellation: zeros everywhere; zeros in shard 1 and
+    negatives in shard 2 (shard 1 predicted wrong); no zeros at all; negatives everywhere; explicit ignore.zero."""
+    from plaid_b200 import _lib as L, sharded
+    from plaid_b200.api import _matrix_struct, _opts
+    P, N, S = 1500, 64, 4300
+    names = synth.gene_names(P)
+    G = synth.genesets_numpy(P, S, seed=52, size_cap=(5, 120))
+    rowmap = pb.make_rowmap(names, names)
+    Xs = synth.sparse_x_numpy(P, N, seed=51)                      # scores >= 0 with exact zeros
+    Xneg = Xs.copy().tolil()
+    Xneg[:, N // 2:] = -Xs[:, N // 2:].toarray()                  # second half: negative scores
+    Xneg = Xneg.tocsc()
+    Dpos = np.abs(synth.dense_x_numpy(P, N, seed=53)) + 0.5       # every score > 0
+    Dall = -Dpos
+    ctxs = [pb.Context(0) for _ in range(2)]
+    for c in ctxs:
+        c.set_genesets(G)
+    Go = O.Named(G, names, [f"s{k}" for k in range(S)])
+    cases = [("zeros", Xs, -1, True), ("zeros+negatives", Xneg, -1, False), ("positive", Dpos, -1, False),
+             ("negative", Dall, -1, False), ("forced on", Xneg, 1, True), ("forced off", Xs, 0, False)]
+    for label, X, izopt, iz_expected in cases:
+        keep = []
+        whole = np.empty((S, N), order="F")
+        o = _opts(ctxs[0].lib, scorer=L.PLAID, out_location=L.HOST, normalize=1, ignore_zero=izopt)
+        ctxs[0].check(ctxs[0].lib.plaidgpu_score(ctxs[0].h, _matrix_struct(X, keep), rowmap.ctypes.data, o, whole.ctypes.data))
+        raw = O.plaid(O.Named(X, names, [f"c{k}" for k in range(N)]), Go, normalize=False).mat
+        want = O.normalize_medians(raw, ignore_zero=None if izopt < 0 else bool(izopt))
+        assert rel_err(whole, want) < 1e-11, label
+        spans = [sharded.shard_columns(N, 2, r) for r in range(2)]
+        outs = [np.empty((S, hi - lo), order="F") for lo, hi in spans]
+        mats = [_matrix_struct(X[:, lo:hi], keep) for lo, hi in spans]
+        opts = [_opts(ctxs[0].lib, scorer=L.PLAID, out_location=L.HOST, normalize=1, ignore_zero=izopt) for _ in spans]
+        scal = sharded.score_multi(ctxs, mats, rowmap, opts, [a.ctypes.data for a in outs], [hi - lo for lo, hi in spans])
+        assert [bool(s.ignore_zero) for s in scal] == [iz_expected] * 2, label
+        assert np.array_equal(np.concatenate(outs, axis=1), whole), label
+        # the full pair is still available on request (computed on demand), and agrees with numpy
+        ma, mz = np.empty(spans[0][1]), np.empty(spans[0][1])
+        tmp = np.empty((S, spans[0][1]), order="F")
+        loc = L.Scalars()
+        c0 = ctxs[0]
+        c0.check(c0.lib.plaidgpu_score_begin(c0.h, mats[0], rowmap.ctypes.data, opts[0], loc))
+        c0.check(c0.lib.plaidgpu_score_compute(c0.h, loc, tmp.ctypes.data))
+        c0.check(c0.lib.plaidgpu_get_col_medians(c0.h, ma.ctypes.data, mz.ctypes.data))
+        r0 = raw[:, :spans[0][1]]
+        assert np.allclose(ma, np.median(r0, axis=0), rtol=1e-12, atol=0), label
+        z = np.where(r0 == 0, np.nan, r0)
+        with np.errstate(all="ignore"):
+            mzo = np.nanmedian(z, axis=0)
+        assert np.allclose(mz, np.where(np.isnan(mzo), 0.0, mzo), rtol=1e-12, atol=0), label
+
+
 def test_gsva_on_column_shards():
     """replaid.gsva on 2 and 3 ragged column shards (threads, one context each): rowtf "ecdf" re-partitions
     the dense shards into row blocks (all-to-all), ranks each gene across ALL samples (plaidgpu_row_ecdf)
