@@ -315,7 +315,6 @@ struct Stats2Smem {
     unsigned long long samp[SAMP];
     unsigned hist[2][NBIN];
   };
-  unsigned long long cand[2][CCAP];  // [bracket][warp][WCAP]: every warp appends to its own segment
   unsigned wcnt[2][NT / 32];
   unsigned long long lo[2], hi[2];
   unsigned below[2], eqlo[2], eqhi[2], ncand[2];
@@ -331,7 +330,11 @@ struct Stats2Smem {
   unsigned long long small[64];
   unsigned part[NT];
   BinHit hit;
+  // [bracket][warp][WCAP]: every warp appends to its own segment.  LAST member: a launch that wants one
+  // median only allocates cand[0] (and uses it for whichever bracket is live) -> more CTAs per SM
+  unsigned long long cand[2][CCAP];
 };
+constexpr size_t STATS2_SMEM_ONE = sizeof(Stats2Smem) - sizeof(unsigned long long) * CCAP;
 
 __device__ void sort_sample(unsigned long long* k, int n) {  // n = power of two, all threads
   for (int size = 2; size <= n; size <<= 1) {
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
     double minv = INFINITY;
     unsigned wc0 = 0, wc1 = 0;  // this warp's candidate counts (warp-uniform)
     unsigned long long* __restrict__ seg0 = s.cand[0] + wid * WCAP;
-    unsigned long long* __restrict__ seg1 = s.cand[1] + wid * WCAP;
+    unsigned long long* __restrict__ seg1 = s.cand[(DO0 && DO1) ? 1 : 0] + wid * WCAP;
     constexpr int UNR = 8;  // loads of 8 rows are issued before any of them is consumed
     for (int l0 = 0; l0 < S; l0 += NT * UNR) {
       double vv[UNR];
@@ -619,7 +622,7 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
       const bool a_in = ka >= e1 && ka < e2, b_in = kb >= e1 && kb < e2;
       if (a_in || b_in) {
         const unsigned qa = a_in ? ka - e1 : kb - e1, qb = b_in ? kb - e1 : ka - e1;
-        select_from_list(s, s.cand[g], s.wcnt[g], nin, qa < qb ? qa : qb, qa < qb ? qb : qa, s.lo[g], s.hi[g], s.res[g]);
+        select_from_list(s, s.cand[(DO0 && DO1) ? g : 0], s.wcnt[g], nin, qa < qb ? qa : qb, qa < qb ? qb : qa, s.lo[g], s.hi[g], s.res[g]);
         // res[g][0] = smaller requested rank, res[g][1] = larger
       }
       __syncthreads();
@@ -775,8 +778,9 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
     if (e != cudaSuccess) return e;
     const void* fast[3] = {(const void*)k_colstats_fast<true, true>, (const void*)k_colstats_fast<true, false>,
                            (const void*)k_colstats_fast<false, true>};
-    for (const void* f : fast) {
-      e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats2Smem));
+    for (int i = 0; i < 3; ++i) {
+      e = cudaFuncSetAttribute(fast[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(i == 0 ? sizeof(Stats2Smem) : STATS2_SMEM_ONE));
       if (e != cudaSuccess) return e;
     }
   }
@@ -794,21 +798,22 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
   cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
+  const size_t smem = which == COLSTATS_BOTH ? sizeof(Stats2Smem) : STATS2_SMEM_ONE;
   if (which == COLSTATS_ALL)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, false>, NT, sizeof(Stats2Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, false>, NT, smem);
   else if (which == COLSTATS_NZ)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<false, true>, NT, sizeof(Stats2Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<false, true>, NT, smem);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, true>, NT, sizeof(Stats2Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, true>, NT, smem);
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > N) grid = N;
   if (which == COLSTATS_ALL)
-    k_colstats_fast<true, false><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+    k_colstats_fast<true, false><<<(unsigned)grid, NT, smem, st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
   else if (which == COLSTATS_NZ)
-    k_colstats_fast<false, true><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+    k_colstats_fast<false, true><<<(unsigned)grid, NT, smem, st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
   else
-    k_colstats_fast<true, true><<<(unsigned)grid, NT, sizeof(Stats2Smem), st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
+    k_colstats_fast<true, true><<<(unsigned)grid, NT, smem, st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   int nfail = 0;

@@ -24,9 +24,7 @@ for i in range(14):
     t1 = time.perf_counter()
     ctx.check(ctx.lib.plaidgpu_score_compute(ctx.h, C.byref(loc), out.data_ptr()))
     t2 = time.perf_counter()
-    ma = np.empty(Nc); mz = np.empty(Nc)
-    ctx.check(ctx.lib.plaidgpu_get_col_medians(ctx.h, ma.ctypes.data, mz.ctypes.data))
-    sharded.combine_medians(ctx.lib, comm, -1, loc, ma, mz)
+    sharded.combine_medians_of(ctx, comm, -1, loc, Nc)
     t3 = time.perf_counter()
     ctx.check(ctx.lib.plaidgpu_score_finish(ctx.h, C.byref(loc), out.data_ptr()))
     torch.cuda.synchronize(); t4 = time.perf_counter()
