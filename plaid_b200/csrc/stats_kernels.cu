@@ -697,6 +697,41 @@ __global__ void __launch_bounds__(256) k_fixup(const double* __restrict__ x, dou
   }
 }
 
+// The same fix-up for a contiguous block of columns (ld == S, S even, 16-byte aligned): the grid walks the
+// block as ONE flat array, consecutive CTAs on consecutive 32 KB pieces, so DRAM sees a single sequential
+// read stream and a single write stream (like a copy) instead of one stream per CTA-owned column.
+constexpr int FIX_CHUNK = 4096;  // elements per CTA iteration (<= S is required: at most one column boundary)
+__global__ void __launch_bounds__(256) k_fixup_flat(const double* __restrict__ x, double* __restrict__ out, int32_t S,
+                                                    int64_t j0, int64_t j1, const double* __restrict__ med, double c,
+                                                    double alpha, const double* __restrict__ beta) {
+  const int64_t total = (j1 - j0) * S;
+  const double2* __restrict__ x2 = reinterpret_cast<const double2*>(x + j0 * S);
+  double2* __restrict__ o2 = reinterpret_cast<double2*>(out + j0 * S);
+  for (int64_t start = (int64_t)blockIdx.x * FIX_CHUNK; start < total; start += (int64_t)gridDim.x * FIX_CHUNK) {
+    const int64_t ja = start / S;                 // column of the first element of this chunk
+    const int64_t bound = (ja + 1) * S;           // first element of the next column
+    const double sa = (med ? -med[j0 + ja] : 0.0) + c;
+    const double sb = (bound < total) ? (med ? -med[j0 + ja + 1] : 0.0) + c : sa;
+    const int32_t ra = (int32_t)(start - ja * S);  // row of the first element
+#pragma unroll
+    for (int u = 0; u < FIX_CHUNK / 2 / 256; ++u) {
+      const int64_t e = start + 2 * (int64_t)(u * 256 + threadIdx.x);
+      if (e >= total) break;
+      double2 v = __ldcs(x2 + (e >> 1));
+      const bool second = e >= bound;             // S is even: both halves of a pair lie in one column
+      const double shift = second ? sb : sa;
+      v.x = alpha * (v.x + shift);
+      v.y = alpha * (v.y + shift);
+      if (beta) {
+        const int32_t r = (int32_t)(e - start) + ra - (second ? S : 0);
+        v.x += beta[r];
+        v.y += beta[r + 1];
+      }
+      __stcs(o2 + (e >> 1), v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_minmax(const double* __restrict__ x, int64_t n,
                                                 unsigned long long* __restrict__ res) {
   unsigned long long lo = ~0ull, hi = 0ull;
@@ -838,6 +873,13 @@ cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ld == S && (S & 1) == 0 && S >= FIX_CHUNK && ((((uintptr_t)(x + j0 * ld)) | ((uintptr_t)(out + j0 * ld))) & 15) == 0) {
+    const int64_t chunks = ((j1 - j0) * (int64_t)S + FIX_CHUNK - 1) / FIX_CHUNK;
+    int64_t grid = (int64_t)sms * 8;
+    if (grid > chunks) grid = chunks;
+    k_fixup_flat<<<(unsigned)grid, 256, 0, st>>>(x, out, S, j0, j1, med, c, alpha, beta);
+    return cudaGetLastError();
+  }
   int64_t grid = (int64_t)sms * 8;
   if (grid > j1 - j0) grid = j1 - j0;
   k_fixup<<<(unsigned)grid, 256, 0, st>>>(x, out, ld, S, j0, j1, med, c, alpha, beta);
