@@ -181,6 +181,48 @@ def test_colranks_nan_and_large_column(gpu_ctx):
     assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
 
 
+def test_colranks_counting_and_sorting_paths_agree(gpu_ctx):
+    """k_rank ranks a column by COUNTING its distinct values when there are at most 448 of them and by sorting
+    otherwise; columns on both sides of that limit (447 / 448 / 449 / 700 distinct values, 12 values, all distinct,
+    negatives + stored zeros + NaN, empty) in one launch must all be bit-exact, for every ranking variant"""
+    rng = np.random.default_rng(21)
+    P = 6000
+    cols = []
+    for nd in (447, 448, 449, 700, 12, None, 3):
+        n = 2500
+        rows = np.sort(rng.choice(P, size=n, replace=False))
+        if nd is None:
+            vals = rng.normal(size=n)  # all distinct
+        else:
+            pool = np.round(rng.normal(size=4 * nd), 6)
+            pool = np.unique(pool)[:nd]
+            assert pool.size == nd
+            vals = np.concatenate([pool, rng.choice(pool, size=n - nd)])  # every pool value at least once
+            rng.shuffle(vals)
+        cols.append((rows, vals))
+    rows, vals = cols[-1]
+    vals[:50] = 0.0        # stored zeros
+    vals[50:60] = np.nan   # NaN entries
+    vals[60:200] *= -1.0
+    cols.append((np.zeros(0, dtype=np.int64), np.zeros(0)))  # an empty column
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r, _ in cols])])
+    X = sp.csc_matrix((np.concatenate([v for _, v in cols]), np.concatenate([r for r, _ in cols]), indptr),
+                      shape=(P, len(cols)))
+
+    def same(a, b):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+    for ties in ("average", "min", "max"):
+        for signed in (False, True):
+            same(pb.sparse_colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx).data,
+                 O.sparse_colranks(X, signed=signed, ties_method=ties).data)
+            same(pb.colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx), O.colranks(X, signed=signed, ties_method=ties))
+    D = X[:, :5].toarray()
+    D[D == 0] = 1.5  # dense input, 6000-row columns: few distinct values -> counting path on dense columns
+    same(pb.colranks(D, ctx=gpu_ctx), O.colranks(D))
+
+
 # ---- normalize_medians ---------------------------------------------------------------------------
 def test_normalize_medians_edge_cases(gpu_ctx):
     rng = np.random.default_rng(4)
