@@ -107,7 +107,10 @@ typedef struct plaidgpu_opts {
                               samples, R/plaid.R:344-346); PLAIDGPU_ROWTF_DONE (2) = X already holds the
                               row-transformed values (column shards: plaidgpu_row_ecdf after the
                               column -> row exchange, see plaid_b200/sharded.py gsva_shard) */
-  int32_t _pad2;
+  int32_t exact_fp64;      /* 0 (default): the block of high-degree rows (sparse X) / every row (dense X) is scored on
+                              the tensor cores in per-column 30-bit fixed point with exact integer accumulation
+                              (|error| <= 2^-31 * max|x_gj| per term, see plaid_b200/csrc/tc_kernels.cu);
+                              1: every add in fp64 (gather + scatter passes only) */
 } plaidgpu_opts;
 
 /* cross-shard scalars.  Produced per shard by *_begin (local values), combined by the
@@ -283,6 +286,9 @@ void* plaidgpu_stream(const plaidgpu_ctx* ctx);
 int plaidgpu_plan_info(const plaidgpu_ctx* ctx, int32_t* tile_sets, int32_t* n_tiles,
                        int64_t* nnz_mapped, int32_t* warps_per_cta, int32_t* ctas,
                        int32_t* gather_block, int32_t* gather_blocks);
+/* the tensor-core block of the current plan: rows of X scored by tcgen05 (0 = the pass is off), the same
+ * padded to whole K blocks of 128, and the number of 8-bit fixed-point digits per value */
+int plaidgpu_tc_info(const plaidgpu_ctx* ctx, int32_t* block_rows, int32_t* padded_rows, int32_t* slices);
 
 /* ---- expression-matrix files (scope row f4) -------------------------------------------
  * The on-disk formats on the input side of the path, decoded on the host into the CSC arrays of a

@@ -33,7 +33,7 @@ class Opts(C.Structure):
                 ("out_location", C.c_int32), ("tile_sets", C.c_int32), ("alpha", C.c_double),
                 ("rmax", C.c_double), ("auc_max_rank", C.c_double), ("tau", C.c_double),
                 ("nrow_x", C.c_int64), ("matg_full_colsums", C.c_void_p), ("row_mean", C.c_void_p),
-                ("row_sd", C.c_void_p), ("gsva_ecdf", C.c_int32), ("_pad2", C.c_int32)]
+                ("row_sd", C.c_void_p), ("gsva_ecdf", C.c_int32), ("exact_fp64", C.c_int32)]
 
 
 class Scalars(C.Structure):
@@ -92,6 +92,7 @@ SYMBOLS = {
     "plaidgpu_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32)]),
+    "plaidgpu_tc_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -128,8 +128,11 @@ class Context:
         nm = C.c_int64()
         self.check(self.lib.plaidgpu_plan_info(self.h, C.byref(ts), C.byref(nt), C.byref(nm), C.byref(wp), C.byref(ct),
                                                C.byref(gk), C.byref(gb)))
+        tr, tp, tsl = (C.c_int32() for _ in range(3))
+        self.check(self.lib.plaidgpu_tc_info(self.h, C.byref(tr), C.byref(tp), C.byref(tsl)))
         return {"tile_sets": ts.value, "n_tiles": nt.value, "nnz_mapped": nm.value, "warps_per_cta": wp.value,
-                "ctas": ct.value, "gather_block": gk.value, "gather_blocks": gb.value}
+                "ctas": ct.value, "gather_block": gk.value, "gather_blocks": gb.value,
+                "tc_rows": tr.value, "tc_rows_padded": tp.value, "tc_slices": tsl.value}
 
 
 _default_ctx: dict = {}
@@ -223,9 +226,15 @@ def make_rowmap(x_rownames: Sequence[str], g_rownames: Sequence[str]) -> np.ndar
     return out
 
 
+# every add in fp64 (plaidgpu_opts.exact_fp64) instead of the tensor-core fixed-point block pass; module-wide
+# default of the Python mirror, overridable per call through opts_kw
+EXACT_FP64 = False
+
+
 def _opts(lib, **kw) -> L.Opts:
     o = L.Opts()
     lib.plaidgpu_default_opts(C.byref(o))
+    o.exact_fp64 = 1 if EXACT_FP64 else 0
     for k, v in kw.items():
         setattr(o, k, v)
     return o

@@ -71,6 +71,9 @@ struct plaidgpu_ctx {
   int32_t gK = 0, gblocks = 0;
   int64_t g_entries = 0;
   DevBuf d_dmap, d_dptr, d_didx, d_colscale;
+  // tensor-core pass over the block (tc_kernels.cu): tcK = block rows padded to a multiple of 128 (0 = off)
+  int32_t tcK = 0, tc_rows = 0, tc_slices = 4;
+  DevBuf d_abits, b_tcB, b_colinv, b_tcflag;
 
   // current scoring call
   bool in_call = false, computed = false;
@@ -148,48 +151,73 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
       }
     }
 
-  // ---- gather blocks ---------------------------------------------------------------------
+  // ---- the block: rows of X that leave the scatter pass ---------------------------------------
+  // sparse X: the highest-degree rows (in single-cell data the ubiquitous genes: nearly dense rows of X that
+  // sit in thousands of sets and carry most of the adds); dense X: every row.  The block is scored on the
+  // tensor cores (tc_kernels.cu) from bit masks of t(G); the fp64 gather passes (blocks of gK local ids,
+  // gather_kernels.cu) cover the same rows when the tensor-core path is off or meets a non-finite entry.
   const int Kmax = gather_max_block(c->device);
+  bool tc_on = true;
+  if (const char* e = getenv("PLAIDGPU_TC")) tc_on = atoi(e) != 0;
   std::vector<uint16_t> dmap;          // sparse mode: row -> local id in the block, 0xFFFF otherwise
-  std::vector<int32_t> blk_of_row;     // row -> block (dense mode) / 0 or -1 (sparse mode)
-  int32_t gK = 0, gblocks = 0;
+  std::vector<int32_t> blk_of_row;     // sparse mode: row -> gather block or -1
+  std::vector<int32_t> local_of_row;   // row -> local id in the block or -1 (both modes)
+  int32_t gK = 0, gblocks = 0, tcK = 0, tc_rows = 0;
   if (dense) {
     gK = std::min<int32_t>(Kmax, ((P + 31) / 32) * 32);
     if (gK <= 0) return fail(c, PLAIDGPU_ERR_CUDA, "no shared memory for the gather tile");
     gblocks = (P + gK - 1) / gK;
+    if (tc_on && S >= 128 && P >= 128) {
+      tc_rows = P;
+      tcK = ((P + 127) / 128) * 128;
+      local_of_row.resize((size_t)P);
+      for (int32_t r = 0; r < P; ++r) local_of_row[r] = r;
+    }
   } else if (Kmax > 0 && S >= 1024 && nnzm >= 100000) {
-    // blocks of the highest-degree rows: in single-cell data these are the ubiquitous genes, i.e. the
-    // rows of X that are nearly dense and carry most of the adds.  Block 0 = ranks [0, K), block 1 =
-    // ranks [K, 2K) ... (each further block costs one more read-modify-write of the output)
-    int want_blocks = 1;  // measured on C4: a 2nd / 3rd block costs more (extra pass over the output) than it saves
-    if (const char* e = getenv("PLAIDGPU_GATHER_BLOCKS")) want_blocks = std::max(0, std::min(8, atoi(e)));
     std::vector<int32_t> order((size_t)P);
     for (int32_t r = 0; r < P; ++r) order[r] = r;
-    const int32_t want = (int32_t)std::min<int64_t>((int64_t)Kmax * want_blocks, P);
-    std::partial_sort(order.begin(), order.begin() + want, order.end(),
-                      [&](int32_t x, int32_t y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
+    std::sort(order.begin(), order.end(),
+              [&](int32_t x, int32_t y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
     int32_t k = 0;
-    while (k < want && deg[order[k]] > 0) ++k;
-    gK = Kmax;
-    gblocks = k / Kmax;                       // full blocks only, except that a single partial block of
-    if (gblocks == 0 && k >= 32) {            // >= 32 rows is still worth a gather pass
-      gblocks = 1;
-      gK = std::min(Kmax, ((k + 31) / 32) * 32);
-    }
-    if (gblocks > 0) {
-      blk_of_row.assign((size_t)P, -1);
-      dmap.assign((size_t)P * gblocks, 0xFFFFu);
-      for (int32_t b = 0; b < gblocks; ++b) {
-        const int32_t lo = b * gK, hi = std::min(k, (b + 1) * gK);
-        std::vector<int32_t> sel(order.begin() + lo, order.begin() + hi);
-        std::sort(sel.begin(), sel.end());  // local ids ascend with the row index (reference sum order)
-        for (size_t i = 0; i < sel.size(); ++i) {
-          dmap[(size_t)b * P + sel[i]] = (uint16_t)i;
-          blk_of_row[sel[i]] = b;
-        }
+    if (tc_on) {
+      // a row costs the tensor-core pass the same whatever its degree, the scatter pass in proportion to it:
+      // rows in at least ~0.55 % of the sets go to the block (3,072 rows on the 30k-set benchmark collection)
+      double frac = 0.0055;
+      if (const char* e = getenv("PLAIDGPU_TC_DEGFRAC")) frac = atof(e);
+      const uint32_t thr = (uint32_t)std::max(32.0, ceil(frac * (double)S));
+      while (k < P && deg[order[k]] >= thr) ++k;
+      k = std::min<int32_t>(k, 8192);
+      if (const char* e = getenv("PLAIDGPU_TC_K")) k = std::max(0, std::min<int32_t>({atoi(e), P, 8192}));
+      k = (k / 128) * 128;  // whole K blocks: the padding of a partial one would be paid for like real rows
+      while (k > 0 && deg[order[k - 1]] == 0) --k;
+      if (k >= 128) {
+        tc_rows = k;
+        tcK = ((k + 127) / 128) * 128;
+      } else {
+        k = 0;
       }
-    } else {
-      gK = 0;
+    }
+    if (k == 0) {  // legacy: one gather block of the Kmax highest-degree rows
+      int want_blocks = 1;  // measured on C4: a 2nd / 3rd block costs more (extra pass over the output) than it saves
+      if (const char* e = getenv("PLAIDGPU_GATHER_BLOCKS")) want_blocks = std::max(0, std::min(8, atoi(e)));
+      const int32_t want = (int32_t)std::min<int64_t>((int64_t)Kmax * want_blocks, P);
+      while (k < want && deg[order[k]] > 0) ++k;
+      if (k >= Kmax) k = (k / Kmax) * Kmax;      // full blocks only, except that a single partial block of
+      else if (k < 32) k = 0;                    // >= 32 rows is still worth a gather pass
+    }
+    if (k > 0) {
+      gK = std::min(Kmax, ((k + 31) / 32) * 32);
+      gblocks = (k + gK - 1) / gK;
+      std::vector<int32_t> sel(order.begin(), order.begin() + k);
+      std::sort(sel.begin(), sel.end());  // local ids ascend with the row index (reference sum order)
+      blk_of_row.assign((size_t)P, -1);
+      local_of_row.assign((size_t)P, -1);
+      dmap.assign((size_t)P, 0xFFFFu);
+      for (size_t i = 0; i < sel.size(); ++i) {
+        dmap[sel[i]] = (uint16_t)i;
+        local_of_row[sel[i]] = (int32_t)i;
+        blk_of_row[sel[i]] = (int32_t)(i / (size_t)gK);
+      }
     }
   }
   // set-major member lists per block, 16-bit local ids, padded to multiples of 4 with gK (a zero row)
@@ -226,7 +254,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         if (r < 0) continue;
         if (dense) didx[pos[(size_t)(r / gK) * S + s]++] = (uint32_t)(r % gK) * 256u;
         else if (blk_of_row[r] >= 0)
-          didx[pos[(size_t)blk_of_row[r] * S + s]++] = (uint32_t)dmap[(size_t)blk_of_row[r] * P + r] * 256u;
+          didx[pos[(size_t)blk_of_row[r] * S + s]++] = (uint32_t)(local_of_row[r] % gK) * 256u;
       }
     for (int32_t b = 0; b < gblocks; ++b)
       for (int32_t s = 0; s < S; ++s) {
@@ -283,6 +311,21 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
     }
     for (int k = 0; k < 8; ++k) idx.push_back((uint16_t)0xFFFFu);
   }
+  // bit masks of t(G) over the block for the tensor-core pass: [set tile][K block][128 set rows] x 128 bits
+  std::vector<uint32_t> abits;
+  if (tcK > 0) {
+    const size_t tiles_m = ((size_t)S + 127) / 128, kbn = (size_t)tcK / 128;
+    abits.assign(tiles_m * kbn * 128 * 4, 0u);
+    for (int32_t s = 0; s < S; ++s)
+      for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+        const int32_t r = g2x[c->Gi[q]];
+        if (r < 0) continue;
+        const int32_t l = local_of_row[r];
+        if (l < 0) continue;
+        const size_t m = (size_t)s >> 7, i = (size_t)s & 127, kb = (size_t)l >> 7, b = (size_t)l & 127;
+        abits[((m * kbn + kb) * 128 + i) * 4 + (b >> 5)] |= 1u << (b & 31);
+      }
+  }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
   for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76
 
@@ -299,11 +342,16 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   CK(up(c->d_dmap, dmap.data(), dmap.size() * sizeof(uint16_t)));
   CK(up(c->d_dptr, dptr.data(), dptr.size() * sizeof(uint32_t)));
   CK(up(c->d_didx, didx.data(), didx.size() * sizeof(uint32_t)));
+  CK(up(c->d_abits, abits.data(), abits.size() * sizeof(uint32_t)));
   CK(cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
   c->Ts = Ts;
   c->T = T;
   c->gK = gK;
   c->gblocks = gblocks;
+  c->tcK = tcK;
+  c->tc_rows = tc_rows;
+  c->tc_slices = 4;
+  if (const char* e = getenv("PLAIDGPU_TC_SLICES")) c->tc_slices = (atoi(e) == 2) ? 2 : 4;
   c->nnz_mapped = nnzm;
   c->plan_P = P;
   c->plan_hint = tile_hint;
@@ -535,7 +583,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
-                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
+                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->d_abits, &c->b_tcB, &c->b_colinv, &c->b_tcflag, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
                     &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list, &c->b_ci, &c->b_cx, &c->b_ce};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -566,10 +614,23 @@ int plaidgpu_plan_info(const plaidgpu_ctx* c, int32_t* tile_sets, int32_t* n_til
   return PLAIDGPU_OK;
 }
 
+int plaidgpu_tc_info(const plaidgpu_ctx* c, int32_t* block_rows, int32_t* padded_rows, int32_t* slices) {
+  if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
+  if (block_rows) *block_rows = c->tcK > 0 ? c->tc_rows : 0;
+  if (padded_rows) *padded_rows = c->tcK;
+  if (slices) *slices = c->tc_slices;
+  return PLAIDGPU_OK;
+}
+
 int plaidgpu_set_genesets(plaidgpu_ctx* c, int32_t P_G, int32_t S, const int32_t* Gp, const int32_t* Gi,
                           const double* Gx) {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (P_G <= 0 || S <= 0 || !Gp || (!Gi && Gp[S] > 0)) return fail(c, PLAIDGPU_ERR_ARG, "bad gene-set matrix");
+  // the same pattern again (an R caller re-registers matG on every call): keep the plan
+  if (c->have_g && !Gx && c->PG == P_G && c->S == S && Gp[0] == 0 && (size_t)Gp[S] == c->Gi.size() &&
+      memcmp(c->Gp.data(), Gp, sizeof(int32_t) * ((size_t)S + 1)) == 0 &&
+      (c->Gi.empty() || memcmp(c->Gi.data(), Gi, sizeof(int32_t) * c->Gi.size()) == 0))
+    return PLAIDGPU_OK;
   c->have_g = false;
   c->plan_ok = false;
   c->PG = P_G;
@@ -835,6 +896,62 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   }
   p.smin = smin;
   CK(cudaEventRecord(c->ev[0], c->stream));
+  // ---- the block (high-degree rows of sparse X / every row of dense X) ----------------------------
+  const bool use_tc = c->tcK > 0 && !o.exact_fp64 && c->N > 0;
+  const int* tc_flag = nullptr;
+  bool compacted = false;
+  if (use_tc) {
+    // tensor cores: fixed-point digit rows of the block (k_tc_prep_*), then t(G) bits x digits (k_tc_score).
+    // A non-finite block entry cannot be quantised: it raises a device flag, the tensor-core kernel returns at
+    // once and the fp64 gather passes below (otherwise no-ops) redo the block.
+    const int sl = c->tc_slices;
+    const int ct = tc_cells_per_tile(sl);
+    CK(c->b_tcflag.reserve(sizeof(int)));
+    CK(cudaMemsetAsync(c->b_tcflag.p, 0, sizeof(int), c->stream));
+    CK(c->b_colinv.reserve((size_t)c->N * sizeof(double)));
+    // column chunks keep the digit-row operand within ~4 GiB whatever N is
+    int64_t chunk = std::max<int64_t>(ct, ((int64_t)(4ll << 30) / ((int64_t)c->tcK * sl)) / ct * ct);
+    if (chunk > c->N) chunk = c->N;
+    CK(c->b_tcB.reserve(tc_operand_bytes(chunk, c->tcK, sl)));
+    if (!c->dense && c->nnz > 0) {
+      CK(c->b_ci.reserve((size_t)c->nnz * sizeof(int32_t)));
+      CK(c->b_cx.reserve((size_t)c->nnz * sizeof(double)));
+      CK(c->b_ce.reserve((size_t)c->N * sizeof(int32_t)));
+    }
+    tc_flag = c->b_tcflag.as<int>();
+    for (int64_t j0 = 0; j0 < c->N; j0 += chunk) {
+      const int64_t nj = std::min<int64_t>(chunk, c->N - j0);
+      if (c->dense) {
+        CK(launch_tc_prep_dense(p.xx + j0 * (int64_t)c->P, c->P, nj, p.mode, p.a0, p.a1, c->tcK, sl,
+                                c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0, c->b_tcflag.as<int>(), c->stream));
+      } else {
+        CK(launch_tc_prep_csc(c->xp + j0, c->xi, p.xx, p.r0 ? p.r0 + j0 : nullptr, c->d_dmap.as<uint16_t>(), nj, p.mode,
+                              p.a0, p.a1, c->tcK, sl, c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0,
+                              c->b_ci.as<int32_t>(), c->b_cx.as<double>(), c->b_ce.as<int32_t>() + j0,
+                              c->b_tcflag.as<int>(), c->stream));
+      }
+      TcParams t{};
+      t.abits = c->d_abits.as<uint4>();
+      t.S = c->S;
+      t.N = nj;
+      t.colinv = c->b_colinv.as<double>() + j0;
+      t.skip_if = tc_flag;
+      t.final = c->dense ? 1 : 0;
+      t.mode = p.mode;
+      t.a0 = p.a0;
+      t.a1 = p.a1;
+      t.r0 = p.r0 ? p.r0 + j0 : nullptr;
+      t.inv = p.inv;
+      t.ns = p.ns;
+      t.colscale = p.colscale ? p.colscale + j0 : nullptr;
+      t.out = c->raw + j0 * (int64_t)c->S;
+      t.ld = c->S;
+      t.smin = smin;
+      CK(launch_tc_score(t, c->b_tcB.as<signed char>(), c->tcK, sl, c->stream));
+      c->launches += 2;
+    }
+    compacted = !c->dense && c->nnz > 0;
+  }
   if (c->gblocks > 0) {
     GatherParams g{};
     g.smin = smin;
@@ -844,7 +961,6 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     g.r0 = p.r0;
     g.P = c->P;
     g.N = c->N;
-
     g.K = c->gK;
     g.didx = c->d_didx.as<uint32_t>();
     g.inv = p.inv;
@@ -856,9 +972,11 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     g.a1 = p.a1;
     g.out = c->raw;
     g.ld = c->S;
+    g.run_if = tc_flag;  // after a tensor-core pass: only when it had to give up
+    g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>();
     for (int32_t b = 0; b < c->gblocks; ++b) {
       g.g0 = b * c->gK;
-      g.dmap = c->dense ? nullptr : c->d_dmap.as<uint16_t>() + (size_t)b * c->P;
+      g.dlo = b * c->gK;
       g.dptr = c->d_dptr.as<uint32_t>() + (size_t)b * (c->S + 1);
       g.accumulate = b > 0;
       g.final = c->dense && (b == c->gblocks - 1);  // sparse X: the scatter pass finishes the scores
@@ -868,14 +986,17 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     p.accumulate = 1;
   }
   if (!c->dense) {
-    if (c->gblocks == 1 && c->nnz > 0) {
-      // the scatter pass never needs the gather block's entries: compact the columns once
+    if (!compacted && c->gblocks > 0 && c->nnz > 0) {
+      // the scatter pass never needs the block's entries: compact the columns once
       CK(c->b_ci.reserve((size_t)c->nnz * sizeof(int32_t)));
       CK(c->b_cx.reserve((size_t)c->nnz * sizeof(double)));
       CK(c->b_ce.reserve((size_t)std::max<int64_t>(c->N, 1) * sizeof(int32_t)));
       CK(launch_compact(c->xp, c->xi, p.xx, c->d_dmap.as<uint16_t>(), c->N, c->b_ci.as<int32_t>(), c->b_cx.as<double>(),
                         c->b_ce.as<int32_t>(), c->stream));
       c->launches += 1;
+      compacted = true;
+    }
+    if (compacted) {
       p.xi = c->b_ci.as<int32_t>();
       p.xx = c->b_cx.as<double>();
       p.xe = c->b_ce.as<int32_t>();

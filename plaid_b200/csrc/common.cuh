@@ -69,7 +69,9 @@ struct GatherParams {
   const double* r0;      // rank scorers: zero-group rank per column, else nullptr
   int32_t P;
   int64_t N;
-  const uint16_t* dmap;  // sparse mode: X row -> local id in the block, 0xFFFF = not in block
+  const uint16_t* dmap;  // sparse mode: X row -> local id in the whole block, 0xFFFF = not in block
+  int32_t dlo;           // sparse mode: this pass covers local ids [dlo, dlo + K)
+  const int* run_if;     // optional device flag: the pass runs only when it is non-zero
   int32_t g0;            // dense mode: block = rows [g0, g0 + K)
   int32_t K;
   const uint32_t* dptr;  // [S + 1] offsets into didx (multiples of 4)
@@ -86,6 +88,27 @@ struct GatherParams {
   double* out;
   int64_t ld;
   unsigned long long* smin;  // as in ScoreParams
+};
+
+// Tensor-core pass over the block (tc_kernels.cu): out[s, j] = 2^-e_j * sum_g A[s, g] * q[g, j], see there.
+struct TcParams {
+  const uint4* abits;    // [ceil(S / 128)][Kp / 128][128] membership masks: bit b of row i = gene (kb*128 + b) in set (m*128 + i)
+  int32_t kblocks;       // Kp / 128 (set by launch_tc_score)
+  int32_t ncell_tiles;   // set by launch_tc_score
+  int32_t S;
+  int64_t N;
+  const double* colinv;  // [N] 2^-e_j: fixed point -> value
+  const int* skip_if;    // device flag: non-zero -> the kernel returns at once (non-finite block entries)
+  // final != 0 (dense X, no scatter pass follows): apply the score epilogue; else store the partial set sums
+  int32_t final, mode;
+  double a0, a1;
+  const double* r0;
+  const double* inv;
+  const double* ns;
+  const double* colscale;
+  double* out;
+  int64_t ld;
+  unsigned long long* smin;
 };
 
 struct LaunchCfg {
@@ -107,6 +130,18 @@ cudaError_t launch_gather(const GatherParams& p, cudaStream_t st);
 // colscale[j] = 100 / (sum_i |f(x_ij)| + 1e-8) (kind 1) or 1 / (mean_i |f(x_ij)| + 1e-8) (kind 2)
 cudaError_t launch_colabs(const int32_t* xp, const double* xx, int32_t P, int64_t N, int mode, double a0,
                           double a1, int kind, double* colscale, cudaStream_t st);
+
+// tc_kernels.cu — tensor-core (tcgen05, int8 fixed point) pass over the block of high-degree rows / dense X
+int tc_cells_per_tile(int slices);
+size_t tc_operand_bytes(int64_t N, int Kp, int slices);  // bytes of the digit-row operand Bd
+// quantise the block rows of a CSC shard into Bd (+ colinv), compact every other entry for the scatter pass
+cudaError_t launch_tc_prep_csc(const int32_t* xp, const int32_t* xi, const double* xx, const double* r0,
+                               const uint16_t* dmap, int64_t N, int mode, double a0, double a1, int Kp, int slices,
+                               signed char* Bd, double* colinv, int32_t* oi, double* ox, int32_t* xe, int* flag,
+                               cudaStream_t st);
+cudaError_t launch_tc_prep_dense(const double* x, int32_t P, int64_t N, int mode, double a0, double a1, int Kp,
+                                 int slices, signed char* Bd, double* colinv, int* flag, cudaStream_t st);
+cudaError_t launch_tc_score(const TcParams& p, const signed char* Bd, int Kp, int slices, cudaStream_t st);
 
 // stats_kernels.cu
 // per-column statistics of a dense S x N matrix (ld = leading dimension):

@@ -29,6 +29,7 @@ constexpr int GPAD = 9;
 
 __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
   extern __shared__ double gsm[];
+  if (p.run_if && *p.run_if == 0) return;  // fallback pass of the tensor-core path: nothing to redo
   double* __restrict__ Xs = gsm;                                   // [(K + 1)][GC]
   double* __restrict__ st = gsm + (size_t)(p.K + 1) * GC;          // [GW][GC][GPAD]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -54,8 +55,8 @@ __global__ void __launch_bounds__(GW * 32, 1) k_gather(const GatherParams p) {
         double fb = 0.0;
         if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
         for (int64_t e = c0 + lane; e < c1; e += 32) {
-          const unsigned d = p.dmap[p.xi[e]];
-          if (d != 0xFFFFu) {
+          const unsigned d = (unsigned)p.dmap[p.xi[e]] - (unsigned)p.dlo;  // local id inside this block
+          if (d < (unsigned)K) {
             double v = xform_value(p.mode, p.xx[e], p.a0, p.a1);
             if (p.mode >= XF_SING) v -= fb;
             Xs[d * GC + c] = v;

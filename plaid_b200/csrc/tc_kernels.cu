@@ -1,0 +1,569 @@
+// K0 — the dense-ish block of the gene-set score product on the 5th-generation tensor cores
+// (reference R/plaid.R:100-123: Matrix::crossprod(G, X) -> CHOLMOD; here only the block of X rows
+// that carry most of the adds, or every row of a dense bulk matrix).
+//
+//   D[set, (cell, slice)] = sum_g  A[set, g] * B[(cell, slice), g]          (tcgen05.mma kind::i8)
+//
+//   A = t(G != 0) restricted to the block's genes: 0/1, exact in int8.  It is never stored as
+//       bytes: the plan keeps it as BIT masks (128 sets x 128 genes = 2 KB per tile) and four
+//       "expander" warps widen one K-block at a time straight into TENSOR MEMORY
+//       (tcgen05.st), which the MMA reads as its A operand — so A costs neither L2 nor
+//       shared-memory bandwidth and the block may hold any number of genes (K is not bounded
+//       by shared memory).
+//   B = the block's rows of X as per-column FIXED POINT: q = rint(x * 2^e_j), |q| < 2^(8 SLICES - 2),
+//       split into SLICES balanced signed base-256 digits, one int8 row per (cell, digit),
+//       K-major ("Bd", written once per call by k_tc_prep_*).  Tiles of 192 rows x 128 genes are
+//       fetched by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an 8-stage ring.
+//   D = int32 accumulators in TMEM (2 x 192 columns, double buffered against the epilogue).
+//       Integer accumulation is EXACT, so the only error of this path is the rounding of x to
+//       fixed point: |err| <= 2^-(8 SLICES - 1) * max_g |x_gj| per term (4 slices: 4.7e-10 relative to the
+//       column's largest block entry; the north star allows 1e-6).  The epilogue recombines the
+//       digits in int64, converts to fp64, undoes the column scale and writes the partial set
+//       sums (or, for dense X where there is no scatter pass, the final scores).
+//
+// Warp roles (320 threads, one CTA per SM): warps 0-3 epilogue (TMEM lanes 32w..32w+31),
+// warps 4-7 expanders (A bits -> TMEM), warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+#include <cuda.h>
+
+#include "common.cuh"
+
+#include <stdlib.h>
+
+#include <algorithm>
+
+namespace plaidgpu {
+
+namespace {
+
+constexpr int TC_M = 128;            // sets per CTA tile (TMEM lanes)
+constexpr int TC_N = 192;            // accumulator columns per tile = cells x slices
+constexpr int TC_KB = 128;           // genes (= bytes of a B row) per K block; one swizzle-128B row
+constexpr int TC_BST = 8;            // B ring stages (shared memory)
+constexpr int TC_AST = 4;            // A ring stages (tensor memory, 32 columns each)
+constexpr int TC_ACOL = 2 * TC_N;    // first TMEM column of the A ring
+constexpr int TC_BSTAGE = TC_N * TC_KB;  // 24,576 bytes
+constexpr int TC_THREADS = 320;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], int8 x int8 -> int32, M = 128, N = 192, K = 32
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+      "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// shared-memory matrix descriptor of one B stage: K-major, 128-byte swizzle, rows of 128 bytes, groups of 8
+// rows 1024 bytes apart (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 |
+// SWIZZLE_128B (2) << 61)
+__device__ __forceinline__ uint64_t b_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = INT8 (1 << 7, 1 << 10),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct TcSmem {
+  unsigned long long b_full[TC_BST], b_empty[TC_BST], a_full[TC_AST], a_empty[TC_AST], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int SLICES>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
+  constexpr int CT = TC_N / SLICES;  // cells per tile
+  if (p.skip_if && *p.skip_if != 0) return;  // non-finite block entries: the fp64 gather passes run instead
+  extern __shared__ uint8_t tc_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = base;
+  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)TC_BST * TC_BSTAGE);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+  if (tid == 9 * 32) {
+    for (int i = 0; i < TC_BST; ++i) {
+      mbar_init(smem_u32(&sm->b_full[i]), 1);
+      mbar_init(smem_u32(&sm->b_empty[i]), 1);
+    }
+    for (int i = 0; i < TC_AST; ++i) {
+      mbar_init(smem_u32(&sm->a_full[i]), 4);
+      mbar_init(smem_u32(&sm->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sm->acc_full[i]), 1);
+      mbar_init(smem_u32(&sm->acc_empty[i]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (w == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&sm->tmem_base);
+
+  const int m = blockIdx.x;
+  const int nct = p.ncell_tiles;
+  const int ct0 = (int)(((int64_t)nct * blockIdx.y) / gridDim.y), ct1 = (int)(((int64_t)nct * (blockIdx.y + 1)) / gridDim.y);
+  const int KBN = p.kblocks;
+
+  if (w == 8) {
+    // ===== TMA producer: B tiles (192 rows x 128 bytes) of cell tile ct, K block kb =====
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int ct = ct0; ct < ct1; ++ct)
+        for (int kb = 0; kb < KBN; ++kb) {
+          mbar_wait(smem_u32(&sm->b_empty[st]), ph ^ 1);
+          mbar_expect_tx(smem_u32(&sm->b_full[st]), TC_BSTAGE);
+          tma_load_2d(smem_u32(sB + (size_t)st * TC_BSTAGE), &tmapB, kb * TC_KB, ct * TC_N, smem_u32(&sm->b_full[st]));
+          if (++st == TC_BST) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (w == 9) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
+        const uint32_t as = t & 1, pacc = (t >> 1) & 1;
+        mbar_wait(smem_u32(&sm->acc_empty[as]), pacc ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem + as * TC_N;
+        for (int kb = 0; kb < KBN; ++kb) {
+          mbar_wait(smem_u32(&sm->a_full[sa]), pa);
+          mbar_wait(smem_u32(&sm->b_full[sb]), pb);
+          tc_fence_after();
+          const uint64_t bd = b_desc(smem_u32(sB + (size_t)sb * TC_BSTAGE));
+          const uint32_t acol = tmem + TC_ACOL + sa * 32;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma_i8_ts(dcol, acol + kk * 8, bd + (uint64_t)(kk * 2), TC_IDESC, (kb | kk) != 0 ? 1u : 0u);
+          tc_commit(smem_u32(&sm->a_empty[sa]));
+          tc_commit(smem_u32(&sm->b_empty[sb]));
+          if (++sa == TC_AST) { sa = 0; pa ^= 1; }
+          if (++sb == TC_BST) { sb = 0; pb ^= 1; }
+        }
+        tc_commit(smem_u32(&sm->acc_full[as]));
+      }
+    }
+  } else if (w >= 4) {
+    // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, one K block (32 columns) per stage =====
+    const int row = (w - 4) * 32 + lane;
+    const uint4* __restrict__ ab = p.abits + (size_t)m * KBN * TC_M + row;
+    const uint32_t lane_base = (uint32_t)((w - 4) * 32) << 16;
+    uint32_t sa = 0, pa = 0;
+    for (int ct = ct0; ct < ct1; ++ct) {
+      uint4 nxt = __ldg(ab);
+      for (int kb = 0; kb < KBN; ++kb) {
+        const uint4 bits = nxt;
+        if (kb + 1 < KBN) nxt = __ldg(ab + (size_t)(kb + 1) * TC_M);
+        uint32_t v[32];
+        const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = (((wd[c >> 3] >> (4 * (c & 7))) & 0xFu) * 0x00204081u) & 0x01010101u;
+        mbar_wait(smem_u32(&sm->a_empty[sa]), pa ^ 1);
+        tc_fence_after();
+        tc_st32(tmem + lane_base + TC_ACOL + sa * 32, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[sa]));
+        if (++sa == TC_AST) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fp64 partial set sums (or final scores) -> global =====
+    const int s = m * TC_M + w * 32 + lane;
+    const bool srow = s < p.S;
+    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    double inv = 1.0, nsv = 0.0;
+    if (p.final && srow) {
+      inv = p.inv[s];
+      nsv = p.ns[s];
+    }
+    double vmin = INFINITY;
+    for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
+      const uint32_t as = t & 1, pacc = (t >> 1) & 1;
+      mbar_wait(smem_u32(&sm->acc_full[as]), pacc);
+      tc_fence_after();
+      const int64_t j0 = (int64_t)ct * CT;
+#pragma unroll 1
+      for (int ch = 0; ch < TC_N / 32; ++ch) {
+        uint32_t v[32];
+        tc_ld32(tmem + lane_base + as * TC_N + ch * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // columns ch*32 .. ch*32+31 = digits of cells (ch*32)/SLICES ... (a cell may straddle two chunks for
+        // SLICES = 3: handled by walking columns, carrying the partial value)
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int col = ch * 32 + q;
+          const int cell = col / SLICES, dg = col - cell * SLICES;
+          // recombine digits: value = sum_d digit_d * 256^d  (int64, exact)
+          static_assert(SLICES == 2 || SLICES == 4, "a cell must not straddle a 32-column chunk");
+          if (dg == SLICES - 1) {
+            long long acc = 0;
+#pragma unroll
+            for (int d = SLICES - 1; d >= 0; --d) acc = acc * 256 + (long long)(int)v[q - (SLICES - 1) + d];
+            const int64_t j = j0 + cell;
+            if (srow && j < p.N) {
+              double val = (double)acc * p.colinv[j];
+              if (p.final) {
+                double fb = 0.0;
+                if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
+                if (p.mode >= XF_SING) val += fb * nsv;
+                val *= inv;
+                if (p.colscale) val *= p.colscale[j];
+                vmin = fmin(vmin, val);
+              }
+              __stcs(p.out + j * p.ld + s, val);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[as]));
+    }
+    if (p.final && p.smin) {
+      unsigned long long k = vmin == INFINITY ? ~0ull : key_of(vmin);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, k, o);
+        k = other < k ? other : k;
+      }
+      if (lane == 0 && k != ~0ull) atomicMin(p.smin, k);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (w == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- B operand: fixed-point digit rows ------------------------------------------------------------
+// Balanced base-256 digits of q (|q| < 2^(8 SLICES - 2)): d_k in [-128, 127], q = sum d_k 256^k.
+template <int SLICES>
+__device__ __forceinline__ void digits_of(long long q, signed char (&d)[SLICES]) {
+#pragma unroll
+  for (int k = 0; k < SLICES; ++k) {
+    const int b = (int)(signed char)(q & 0xFF);
+    d[k] = (signed char)b;
+    q = (q - b) >> 8;
+  }
+}
+// scale exponent: 2^e * maxabs < 2^(8 SLICES - 2)
+__device__ __forceinline__ int scale_exp(double maxabs, int slices) {
+  if (!(maxabs > 0.0)) return 0;
+  int ex;
+  frexp(maxabs, &ex);  // maxabs = f * 2^ex, f in [0.5, 1)
+  return (8 * slices - 2) - ex;
+}
+
+// Sparse X: one warp per column.  Entries of the block's rows are quantised into the column's SLICES digit rows
+// (assembled in shared memory, written out with 16-byte stores); every other entry is appended to the compacted
+// column the scatter pass walks (as k_compact does).  flag[0] is raised when a block entry is not finite.
+template <int SLICES>
+__global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__ xp, const int32_t* __restrict__ xi,
+                                                     const double* __restrict__ xx, const double* __restrict__ r0,
+                                                     const uint16_t* __restrict__ dmap, int64_t N, int mode, double a0,
+                                                     double a1, int Kp, signed char* __restrict__ Bd,
+                                                     double* __restrict__ colinv, int32_t* __restrict__ oi,
+                                                     double* __restrict__ ox, int32_t* __restrict__ xe,
+                                                     int* __restrict__ flag) {
+  extern __shared__ uint8_t prep_sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+  signed char* rows = reinterpret_cast<signed char*>(prep_sm) + (size_t)w * SLICES * Kp;  // [SLICES][Kp]
+  const unsigned lt = (1u << lane) - 1u;
+  const int vecs = SLICES * Kp / 16;
+  for (int64_t j = (int64_t)blockIdx.x * W + w; j < N; j += (int64_t)gridDim.x * W) {
+    for (int i = lane; i < vecs; i += 32) reinterpret_cast<uint4*>(rows)[i] = make_uint4(0, 0, 0, 0);
+    const int32_t c0 = xp[j], c1 = xp[j + 1];
+    double fb = 0.0;
+    if (mode >= XF_SING) fb = xform_value(mode, r0 ? r0[j] : 0.0, a0, a1);
+    // pass 1: largest |value| among the block entries of this column
+    double mx = 0.0;
+    bool bad = false;
+    for (int32_t e = c0 + lane; e < c1; e += 32) {
+      if (dmap[xi[e]] != 0xFFFFu) {
+        double v = xform_value(mode, xx[e], a0, a1);
+        if (mode >= XF_SING) v -= fb;
+        const double a = fabs(v);
+        if (!(a <= 1.0e300)) bad = true;  // NaN or Inf
+        mx = fmax(mx, a);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    if (__any_sync(FULL, bad)) {
+      if (lane == 0) atomicExch(flag, 1);
+      mx = 0.0;
+    }
+    const int ex = scale_exp(mx, SLICES);
+    const double sc = ldexp(1.0, ex);
+    if (lane == 0) colinv[j] = ldexp(1.0, -ex);
+    __syncwarp();
+    // pass 2: digits of the block entries, compaction of the rest
+    int32_t o = c0;
+    for (int32_t b = c0; b < c1; b += 32) {
+      const int32_t e = b + lane;
+      int32_t r = 0;
+      double x = 0.0;
+      bool keep = false;
+      if (e < c1) {
+        r = xi[e];
+        x = xx[e];
+        const unsigned d = dmap[r];
+        keep = d == 0xFFFFu;
+        if (!keep) {
+          double v = xform_value(mode, x, a0, a1);
+          if (mode >= XF_SING) v -= fb;
+          const long long q = (fabs(v) <= 1.0e300) ? __double2ll_rn(v * sc) : 0ll;
+          signed char dg[SLICES];
+          digits_of<SLICES>(q, dg);
+#pragma unroll
+          for (int k = 0; k < SLICES; ++k) rows[k * Kp + d] = dg[k];
+        }
+      }
+      const unsigned mk = __ballot_sync(FULL, keep);
+      if (keep) {
+        const int32_t q = o + __popc(mk & lt);
+        oi[q] = r;
+        ox[q] = x;
+      }
+      o += __popc(mk);
+    }
+    if (lane == 0) xe[j] = o;
+    __syncwarp();
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(Bd + (size_t)j * SLICES * Kp);
+    for (int i = lane; i < vecs; i += 32) dst[i] = reinterpret_cast<const uint4*>(rows)[i];
+    __syncwarp();
+  }
+}
+
+// Dense X (column-major P x N, every row is in the block, local id = row): one CTA per column.
+template <int SLICES>
+__global__ void __launch_bounds__(256) k_tc_prep_dense(const double* __restrict__ x, int32_t P, int64_t N, int mode,
+                                                       double a0, double a1, int Kp, signed char* __restrict__ Bd,
+                                                       double* __restrict__ colinv, int* __restrict__ flag) {
+  __shared__ double red[8];
+  __shared__ int sbad;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+    const double* __restrict__ col = x + j * (int64_t)P;
+    if (tid == 0) sbad = 0;
+    __syncthreads();
+    double mx = 0.0;
+    bool bad = false;
+    for (int r = tid; r < P; r += 256) {
+      const double a = fabs(xform_value(mode, col[r], a0, a1));
+      if (!(a <= 1.0e300)) bad = true;
+      mx = fmax(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    if (lane == 0) red[w] = mx;
+    if (bad) sbad = 1;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i]);
+    if (sbad) {
+      if (tid == 0) atomicExch(flag, 1);
+      mx = 0.0;
+    }
+    const int ex = scale_exp(mx, SLICES);
+    const double sc = ldexp(1.0, ex);
+    if (tid == 0) colinv[j] = ldexp(1.0, -ex);
+    signed char* __restrict__ rows = Bd + (size_t)j * SLICES * Kp;
+    // 16 consecutive genes per thread: one 16-byte store per digit row
+    for (int g0 = tid * 16; g0 < Kp; g0 += 256 * 16) {
+      signed char dg[SLICES][16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = g0 + u;
+        long long q = 0;
+        if (r < P) {
+          const double v = xform_value(mode, col[r], a0, a1);
+          q = (fabs(v) <= 1.0e300) ? __double2ll_rn(v * sc) : 0ll;
+        }
+        signed char d1[SLICES];
+        digits_of<SLICES>(q, d1);
+#pragma unroll
+        for (int k = 0; k < SLICES; ++k) dg[k][u] = d1[k];
+      }
+#pragma unroll
+      for (int k = 0; k < SLICES; ++k) *reinterpret_cast<uint4*>(rows + (size_t)k * Kp + g0) = *reinterpret_cast<const uint4*>(dg[k]);
+    }
+    __syncthreads();
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+size_t tc_smem_bytes() { return (size_t)TC_BST * TC_BSTAGE + sizeof(TcSmem) + 1024; }
+
+}  // namespace
+
+int tc_cells_per_tile(int slices) { return TC_N / slices; }
+
+size_t tc_operand_bytes(int64_t N, int Kp, int slices) {
+  const int ct = TC_N / slices;
+  const int64_t tiles = (N + ct - 1) / ct;
+  return (size_t)tiles * TC_N * (size_t)Kp;
+}
+
+cudaError_t launch_tc_prep_csc(const int32_t* xp, const int32_t* xi, const double* xx, const double* r0,
+                               const uint16_t* dmap, int64_t N, int mode, double a0, double a1, int Kp, int slices,
+                               signed char* Bd, double* colinv, int32_t* oi, double* ox, int32_t* xe, int* flag,
+                               cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  if (slices != 2 && slices != 4) return cudaErrorInvalidValue;
+  const size_t per_warp = (size_t)slices * Kp;
+  int warps = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+  if (warps < 1) return cudaErrorInvalidValue;
+  const size_t smem = per_warp * warps;
+  const void* fn = slices == 2 ? (const void*)k_tc_prep_csc<2> : (const void*)k_tc_prep_csc<4>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int64_t grid = (N + warps - 1) / warps;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (slices == 2)
+    k_tc_prep_csc<2><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag);
+  else
+    k_tc_prep_csc<4><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_prep_dense(const double* x, int32_t P, int64_t N, int mode, double a0, double a1, int Kp,
+                                 int slices, signed char* Bd, double* colinv, int* flag, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  if (slices != 2 && slices != 4) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)std::min<int64_t>(N, 148 * 8);
+  if (slices == 2) k_tc_prep_dense<2><<<grid, 256, 0, st>>>(x, P, N, mode, a0, a1, Kp, Bd, colinv, flag);
+  else k_tc_prep_dense<4><<<grid, 256, 0, st>>>(x, P, N, mode, a0, a1, Kp, Bd, colinv, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_score(const TcParams& p0, const signed char* Bd, int Kp, int slices, cudaStream_t st) {
+  if (p0.N <= 0) return cudaSuccess;
+  if (slices != 2 && slices != 4) return cudaErrorInvalidValue;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  TcParams p = p0;
+  const int ct = TC_N / slices;
+  p.ncell_tiles = (int)((p.N + ct - 1) / ct);
+  p.kblocks = Kp / TC_KB;
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)p.ncell_tiles * TC_N};
+  const cuuint64_t gstr[1] = {(cuuint64_t)Kp};
+  const cuuint32_t box[2] = {TC_KB, TC_N};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char*>(Bd), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_bytes();
+  const void* fn = slices == 2 ? (const void*)k_tc_score<2> : (const void*)k_tc_score<4>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_m = (p.S + TC_M - 1) / TC_M;
+  // cell splits: fill whole waves of one CTA per SM (every CTA re-expands A for its own cell tiles, so fewer,
+  // longer CTAs are better as long as the last wave is full)
+  int best = 1;
+  double best_eff = 0.0;
+  for (int cs = 1; cs <= 64 && cs <= p.ncell_tiles; ++cs) {
+    const int64_t ctas = (int64_t)tiles_m * cs;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = cs;
+    }
+  }
+  if (const char* e2 = getenv("PLAIDGPU_TC_CSPLIT")) best = std::max(1, std::min(atoi(e2), p.ncell_tiles));
+  dim3 grid((unsigned)tiles_m, (unsigned)best);
+  if (slices == 2) k_tc_score<2><<<grid, TC_THREADS, smem, st>>>(map, p);
+  else k_tc_score<4><<<grid, TC_THREADS, smem, st>>>(map, p);
+  return cudaGetLastError();
+}
+
+}  // namespace plaidgpu
