@@ -21,8 +21,10 @@
 //       digits in int64, converts to fp64, undoes the column scale and writes the partial set
 //       sums (or, for dense X where there is no scatter pass, the final scores).
 //
-// Warp roles (320 threads, one CTA per SM): warps 0-3 epilogue (TMEM lanes 32w..32w+31),
-// warps 4-7 expanders (A bits -> TMEM), warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+// Warp roles (448 threads, one CTA per SM): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warps 4-11 expanders
+// (A bits -> TMEM; two groups of four warps take alternate K blocks — one group alone could not keep up with the
+// MMA: ncu showed the issuer waiting on A 9 polls per K block, tensor pipe 49 %), warp 12 TMA producer, warp 13
+// MMA issuer + TMEM allocator.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -42,7 +44,8 @@ constexpr int TC_BST = 8;            // B ring stages (shared memory)
 constexpr int TC_AST = 4;            // A ring stages (tensor memory, 32 columns each)
 constexpr int TC_ACOL = 2 * TC_N;    // first TMEM column of the A ring
 constexpr int TC_BSTAGE = TC_N * TC_KB;  // 24,576 bytes
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
+constexpr int TC_W_TMA = 12, TC_W_MMA = 13;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
   TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)TC_BST * TC_BSTAGE);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
-  if (tid == 9 * 32) {
+  if (tid == TC_W_MMA * 32) {
     for (int i = 0; i < TC_BST; ++i) {
       mbar_init(smem_u32(&sm->b_full[i]), 1);
       mbar_init(smem_u32(&sm->b_empty[i]), 1);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (w == 9) {
+  if (w == TC_W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm->tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
   const int ct0 = (int)(((int64_t)nct * blockIdx.y) / gridDim.y), ct1 = (int)(((int64_t)nct * (blockIdx.y + 1)) / gridDim.y);
   const int KBN = p.kblocks;
 
-  if (w == 8) {
+  if (w == TC_W_TMA) {
     // ===== TMA producer: B tiles (192 rows x 128 bytes) of cell tile ct, K block kb =====
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
           if (++st == TC_BST) { st = 0; ph ^= 1; }
         }
     }
-  } else if (w == 9) {
+  } else if (w == TC_W_MMA) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
@@ -210,28 +213,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     }
   } else if (w >= 4) {
     // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, one K block (32 columns) per stage =====
-    const int row = (w - 4) * 32 + lane;
+    // group g (warps 4-7 / 8-11) widens the K blocks q = g, g + 2, ... of this CTA's (cell tile, K block) sequence
+    const int grp = (w - 4) >> 2, wq = (w - 4) & 3;
+    const int row = wq * 32 + lane;
     const uint4* __restrict__ ab = p.abits + (size_t)m * KBN * TC_M + row;
-    const uint32_t lane_base = (uint32_t)((w - 4) * 32) << 16;
-    uint32_t sa = 0, pa = 0;
-    for (int ct = ct0; ct < ct1; ++ct) {
-      uint4 nxt = __ldg(ab);
-      for (int kb = 0; kb < KBN; ++kb) {
-        const uint4 bits = nxt;
-        if (kb + 1 < KBN) nxt = __ldg(ab + (size_t)(kb + 1) * TC_M);
-        uint32_t v[32];
-        const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const int64_t total = (int64_t)(ct1 - ct0) * KBN;
+    int kb = grp % KBN;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (grp < total) nxt = __ldg(ab + (size_t)kb * TC_M);
+    for (int64_t q = grp; q < total; q += 2) {
+      const uint4 bits = nxt;
+      kb += 2;
+      while (kb >= KBN) kb -= KBN;
+      if (q + 2 < total) nxt = __ldg(ab + (size_t)kb * TC_M);
+      uint32_t v[32];
+      const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = (((wd[c >> 3] >> (4 * (c & 7))) & 0xFu) * 0x00204081u) & 0x01010101u;
-        mbar_wait(smem_u32(&sm->a_empty[sa]), pa ^ 1);
-        tc_fence_after();
-        tc_st32(tmem + lane_base + TC_ACOL + sa * 32, v);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[sa]));
-        if (++sa == TC_AST) { sa = 0; pa ^= 1; }
-      }
+      for (int c = 0; c < 32; ++c) v[c] = (((wd[c >> 3] >> (4 * (c & 7))) & 0xFu) * 0x00204081u) & 0x01010101u;
+      const uint32_t sa = (uint32_t)(q & (TC_AST - 1)), pa = (uint32_t)((q / TC_AST) & 1);
+      mbar_wait(smem_u32(&sm->a_empty[sa]), pa ^ 1);
+      tc_fence_after();
+      tc_st32(tmem + lane_base + TC_ACOL + sa * 32, v);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[sa]));
     }
   } else {
     // ===== epilogue: TMEM -> registers -> fp64 partial set sums (or final scores) -> global =====
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (w == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (w == TC_W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // ---- B operand: fixed-point digit rows ------------------------------------------------------------
