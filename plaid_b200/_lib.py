@@ -118,7 +118,7 @@ def load():
         raise ImportError(
             f"{_LIB_PATH} not found: build it with `make -C plaid_b200/csrc` "
             "(or __graft_entry__.build()). plaid_b200 has no CPU fallback.")
-    lib = C.CDLL(_LIB_PATH)
+    lib = C.CDLL(os.environ.get("PLAIDGPU_LIB", _LIB_PATH))  # PLAIDGPU_LIB: development builds only
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res

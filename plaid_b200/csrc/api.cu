@@ -167,7 +167,7 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
     gK = std::min<int32_t>(Kmax, ((P + 31) / 32) * 32);
     if (gK <= 0) return fail(c, PLAIDGPU_ERR_CUDA, "no shared memory for the gather tile");
     gblocks = (P + gK - 1) / gK;
-    if (tc_on && S >= 128 && P >= 128) {
+    if (tc_on && S >= 128 && P >= 128 && P <= 32768) {  // 128 * Kp must stay below 2^22 (tc epilogue)
       tc_rows = P;
       tcK = ((P + 127) / 128) * 128;
       local_of_row.resize((size_t)P);
@@ -322,8 +322,10 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         if (r < 0) continue;
         const int32_t l = local_of_row[r];
         if (l < 0) continue;
-        const size_t m = (size_t)s >> 7, i = (size_t)s & 127, kb = (size_t)l >> 7, b = (size_t)l & 127;
-        abits[((m * kbn + kb) * 128 + i) * 4 + (b >> 5)] |= 1u << (b & 31);
+        // gene t of a 32-gene word sits at bit 8 (t mod 4) + t / 4: the expander's (w >> k) & 0x01010101 then
+        // yields TMEM column k = genes 4k .. 4k+3 as four 0/1 bytes
+        const size_t m = (size_t)s >> 7, i = (size_t)s & 127, kb = (size_t)l >> 7, b = (size_t)l & 127, t = b & 31;
+        abits[((m * kbn + kb) * 128 + i) * 4 + (b >> 5)] |= 1u << (8 * (t & 3) + (t >> 2));
       }
   }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);

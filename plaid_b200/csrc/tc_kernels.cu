@@ -44,8 +44,11 @@ constexpr int TC_BST = 8;            // B ring stages (shared memory)
 constexpr int TC_AST = 4;            // A ring stages (tensor memory, 32 columns each)
 constexpr int TC_ACOL = 2 * TC_N;    // first TMEM column of the A ring
 constexpr int TC_BSTAGE = TC_N * TC_KB;  // 24,576 bytes
-constexpr int TC_THREADS = 448;
-constexpr int TC_W_TMA = 12, TC_W_MMA = 13;
+#ifndef TC_EXP_GROUPS
+#define TC_EXP_GROUPS 1              // expander groups of four warps (group g widens K blocks g, g + GROUPS, ...)
+#endif
+constexpr int TC_W_TMA = 4 + 4 * TC_EXP_GROUPS, TC_W_MMA = TC_W_TMA + 1;
+constexpr int TC_THREADS = 32 * (TC_W_MMA + 1);
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +83,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -175,43 +183,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
 
   if (w == TC_W_TMA) {
     // ===== TMA producer: B tiles (192 rows x 128 bytes) of cell tile ct, K block kb =====
-    if (lane == 0) {
-      uint32_t st = 0, ph = 0;
-      for (int ct = ct0; ct < ct1; ++ct)
-        for (int kb = 0; kb < KBN; ++kb) {
-          mbar_wait(smem_u32(&sm->b_empty[st]), ph ^ 1);
+    uint32_t st = 0, ph = 0;
+    for (int ct = ct0; ct < ct1; ++ct)
+      for (int kb = 0; kb < KBN; ++kb) {
+        mbar_wait(smem_u32(&sm->b_empty[st]), ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(smem_u32(&sm->b_full[st]), TC_BSTAGE);
           tma_load_2d(smem_u32(sB + (size_t)st * TC_BSTAGE), &tmapB, kb * TC_KB, ct * TC_N, smem_u32(&sm->b_full[st]));
-          if (++st == TC_BST) { st = 0; ph ^= 1; }
         }
-    }
+        __syncwarp();
+        if (++st == TC_BST) { st = 0; ph ^= 1; }
+      }
   } else if (w == TC_W_MMA) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
-        const uint32_t as = t & 1, pacc = (t >> 1) & 1;
-        mbar_wait(smem_u32(&sm->acc_empty[as]), pacc ^ 1);
+    // ===== MMA issuer: the whole warp walks the barriers, one elected lane issues (elect.sync keeps the
+    // tcgen05 operands in uniform registers; under `if (lane == 0)` ptxas wrapped every tcgen05 instruction in an
+    // elect / branch loop and the ~100-instruction issue path, not the tensor pipe, set the pace) =====
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    const uint64_t bd0 = b_desc(smem_u32(sB));
+    for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
+      const uint32_t as = t & 1, pacc = (t >> 1) & 1;
+      mbar_wait(smem_u32(&sm->acc_empty[as]), pacc ^ 1);
+      tc_fence_after();
+      const uint32_t dcol = tmem + as * TC_N;
+      for (int kb = 0; kb < KBN; ++kb) {
+        mbar_wait(smem_u32(&sm->a_full[sa]), pa);
+        mbar_wait(smem_u32(&sm->b_full[sb]), pb);
         tc_fence_after();
-        const uint32_t dcol = tmem + as * TC_N;
-        for (int kb = 0; kb < KBN; ++kb) {
-          mbar_wait(smem_u32(&sm->a_full[sa]), pa);
-          mbar_wait(smem_u32(&sm->b_full[sb]), pb);
-          tc_fence_after();
-          const uint64_t bd = b_desc(smem_u32(sB + (size_t)sb * TC_BSTAGE));
+        if (elect_one()) {
+          const uint64_t bd = bd0 + (uint64_t)(sb * (TC_BSTAGE >> 4));
           const uint32_t acol = tmem + TC_ACOL + sa * 32;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             tc_mma_i8_ts(dcol, acol + kk * 8, bd + (uint64_t)(kk * 2), TC_IDESC, (kb | kk) != 0 ? 1u : 0u);
           tc_commit(smem_u32(&sm->a_empty[sa]));
           tc_commit(smem_u32(&sm->b_empty[sb]));
-          if (++sa == TC_AST) { sa = 0; pa ^= 1; }
-          if (++sb == TC_BST) { sb = 0; pb ^= 1; }
         }
-        tc_commit(smem_u32(&sm->acc_full[as]));
+        __syncwarp();
+        if (++sa == TC_AST) { sa = 0; pa ^= 1; }
+        if (++sb == TC_BST) { sb = 0; pb ^= 1; }
       }
+      if (elect_one()) tc_commit(smem_u32(&sm->acc_full[as]));
+      __syncwarp();
     }
-  } else if (w >= 4) {
+  } else if (w >= 4 && w < TC_W_TMA) {
     // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, one K block (32 columns) per stage =====
     // group g (warps 4-7 / 8-11) widens the K blocks q = g, g + 2, ... of this CTA's (cell tile, K block) sequence
     const int grp = (w - 4) >> 2, wq = (w - 4) & 3;
@@ -222,15 +236,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     int kb = grp % KBN;
     uint4 nxt = make_uint4(0, 0, 0, 0);
     if (grp < total) nxt = __ldg(ab + (size_t)kb * TC_M);
-    for (int64_t q = grp; q < total; q += 2) {
+    for (int64_t q = grp; q < total; q += TC_EXP_GROUPS) {
       const uint4 bits = nxt;
-      kb += 2;
+      kb += TC_EXP_GROUPS;
       while (kb >= KBN) kb -= KBN;
-      if (q + 2 < total) nxt = __ldg(ab + (size_t)kb * TC_M);
+      if (q + TC_EXP_GROUPS < total) nxt = __ldg(ab + (size_t)kb * TC_M);
       uint32_t v[32];
       const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = (((wd[c >> 3] >> (4 * (c & 7))) & 0xFu) * 0x00204081u) & 0x01010101u;
+      for (int c = 0; c < 32; ++c) v[c] = (wd[c >> 3] >> (c & 7)) & 0x01010101u;  // bit 8b + k of a word = byte b of column k
       const uint32_t sa = (uint32_t)(q & (TC_AST - 1)), pa = (uint32_t)((q / TC_AST) & 1);
       mbar_wait(smem_u32(&sm->a_empty[sa]), pa ^ 1);
       tc_fence_after();
@@ -256,37 +270,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       mbar_wait(smem_u32(&sm->acc_full[as]), pacc);
       tc_fence_after();
       const int64_t j0 = (int64_t)ct * CT;
+      const bool full = j0 + CT <= p.N;  // warp-uniform: only the last cell tile is ragged
+      double* __restrict__ optr = p.out + j0 * p.ld + s;
+      const double* __restrict__ civ = p.colinv + j0;
 #pragma unroll 1
       for (int ch = 0; ch < TC_N / 32; ++ch) {
         uint32_t v[32];
         tc_ld32(tmem + lane_base + as * TC_N + ch * 32, v);
+        constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
+        double ci[CPC];
+#pragma unroll
+        for (int c = 0; c < CPC; ++c) {
+          const int cell = ch * CPC + c;
+          ci[c] = (full || j0 + cell < p.N) ? __ldg(civ + cell) : 0.0;
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // columns ch*32 .. ch*32+31 = digits of cells (ch*32)/SLICES ... (a cell may straddle two chunks for
-        // SLICES = 3: handled by walking columns, carrying the partial value)
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int col = ch * 32 + q;
-          const int cell = col / SLICES, dg = col - cell * SLICES;
-          // recombine digits: value = sum_d digit_d * 256^d  (int64, exact)
-          static_assert(SLICES == 2 || SLICES == 4, "a cell must not straddle a 32-column chunk");
-          if (dg == SLICES - 1) {
-            long long acc = 0;
-#pragma unroll
-            for (int d = SLICES - 1; d >= 0; --d) acc = acc * 256 + (long long)(int)v[q - (SLICES - 1) + d];
+        for (int c = 0; c < CPC; ++c) {
+          const int cell = ch * CPC + c;
+          // digits -> value: pairs of digits recombine exactly in int32 (|digit sum| <= 128 Kp <= 2^22), the rest in
+          // fp64 (every partial result is an integer below 2^53 times a power of two: no rounding anywhere)
+          const int lo = (int)v[SLICES * c] + ((int)v[SLICES * c + 1] << 8);
+          double val = (double)lo * ci[c];
+          if (SLICES == 4) {
+            const int hi = (int)v[SLICES * c + 2] + ((int)v[SLICES * c + 3] << 8);
+            val = fma((double)hi, 65536.0 * ci[c], val);
+          }
+          if (p.final) {
             const int64_t j = j0 + cell;
-            if (srow && j < p.N) {
-              double val = (double)acc * p.colinv[j];
-              if (p.final) {
-                double fb = 0.0;
-                if (p.mode >= XF_SING) fb = xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1);
-                if (p.mode >= XF_SING) val += fb * nsv;
-                val *= inv;
-                if (p.colscale) val *= p.colscale[j];
-                vmin = fmin(vmin, val);
-              }
-              __stcs(p.out + j * p.ld + s, val);
+            if (srow && (full || j < p.N)) {
+              if (p.mode >= XF_SING) val += xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1) * nsv;
+              val *= inv;
+              if (p.colscale) val *= p.colscale[j];
+              vmin = fmin(vmin, val);
             }
           }
+          if (srow && (full || j0 + cell < p.N)) __stcs(optr + (int64_t)cell * p.ld, val);
         }
       }
       tc_fence_before();
