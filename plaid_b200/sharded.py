@@ -69,7 +69,9 @@ class ThreadComm:
         s = self._s
         s["slots"][self.rank] = v
         s["barrier"].wait()
-        vals = list(s["slots"])
+        # copy before the release: a rank may overwrite the array it contributed (gsva_shard reuses `part`)
+        # as soon as the second barrier lets it go, while a slower rank is still summing the references
+        vals = [x.copy() if isinstance(x, np.ndarray) else x for x in s["slots"]]
         s["barrier"].wait()
         return vals
 
