@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU reference arm (oracle port)
 
-Workload (named in `config.workload`): BASELINE.json configs[3] — plaid() on a 1M-cell x 20k-gene
+Workloads (`--workload`, named in `config.workload`): default "plaid" = BASELINE.json configs[3] — plaid() on a 1M-cell x 20k-gene
 sparse single-cell matrix with 30k gene sets, sample-sharded over 8 B200 — run as its per-GPU
 shard: 125,000 cells per GPU ("weak" scaling: N GPUs score N x 125,000 cells; N = 8 is C4 exactly).
 One step = one full plaid(X, matG) (stats="mean", normalize=TRUE: score product + median
@@ -16,6 +16,10 @@ normalisation) over the rank's shard.
   roofline   dominant kernel (k_score): algorithmic bytes of SURVEY.md §8(d) per launch / CUDA-event
              duration of that launch (events on the library's own stream), vs MEASURED_PEAKS.json;
   cpu_baseline  the oracle (numpy/scipy restatement of the R path) on 1 host core, bounded sample.
+
+Other workloads (same JSON line, same keys): "ssgsea" / "ucell" = replaid.ssgsea(alpha=0) / replaid.ucell on the
+same sparse shard (BASELINE.json configs[2] / configs[4], the north star's second target), "plaid_dense" =
+plaid() on a dense 20,000 x 1,000 bulk matrix (configs[1]; N GPUs run N replicas).
 """
 from __future__ import annotations
 
@@ -45,7 +49,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
-    ap.add_argument("--e2e-cells", type=int, default=32768, help="cells per GPU of the host-buffer e2e leg (0 = skip)")
+    ap.add_argument("--workload", default="plaid", choices=["plaid", "ssgsea", "ucell", "plaid_dense"])
+    ap.add_argument("--e2e-cells", type=int, default=-1,
+                    help="cells per GPU of the host-buffer e2e legs (-1 = the full shard when host memory allows, 0 = skip)")
     ap.add_argument("--cpu-cells", type=int, default=3000, help="cells of the 1-core CPU baseline sample (0 = skip)")
     return ap.parse_args()
 
@@ -208,8 +214,8 @@ def run_ours(a):
 
     # ---- e2e: public API, HOST pinned buffers, H2D + D2H inside the timed region ---------------------
     e2e = None
-    if a.e2e_cells > 0:
-        Ne = min(a.e2e_cells, Nc)
+    if a.e2e_cells != 0:
+        Ne = min(a.e2e_cells if a.e2e_cells > 0 else 32768, Nc)
         hp = torch.empty(Ne + 1, dtype=torch.int32).pin_memory()
         hp.copy_(xp[:Ne + 1])
         ne = int(hp[Ne])

@@ -155,6 +155,16 @@ int plaidgpu_set_genesets(plaidgpu_ctx* ctx, int32_t P_G, int32_t S, const int32
 int plaidgpu_score(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, const int32_t* rowmap,
                    const plaidgpu_opts* opts, double* out);
 
+/* The same call over n devices from ONE host process (an R session): ctxs[0..n) are contexts on
+ * different devices, each with the same gene sets registered.  X and out are HOST buffers; the
+ * columns are split into n contiguous shards (the loop axis of chunked_crossprod, R/plaid.R:110-119),
+ * one host thread drives each context, every shard's block lands directly in `out`, and the
+ * cross-shard scalars (min / max of X, max rank, min score, the column medians and their mean,
+ * gsva row means / SDs) are combined on the host in column order, so the result equals the
+ * single-context one bit for bit.  gsva rowtf = "ecdf" needs one context. */
+int plaidgpu_score_multi(plaidgpu_ctx* const* ctxs, int n, const plaidgpu_matrix* X,
+                         const int32_t* rowmap, const plaidgpu_opts* opts, double* out);
+
 /* Sharded protocol (columns of X split over several contexts / GPUs / processes):
  *   1. every shard: plaidgpu_score_begin(ctx, X_shard, rowmap, opts, &local)
  *        uploads / ranks the shard and reports x_min, x_max, rank_max;

@@ -240,8 +240,11 @@ def _opts(lib, **kw) -> L.Opts:
     return o
 
 
-def _score(X: NamedMatrix, matG: NamedMatrix, opts_kw: dict, ctx: Optional[Context], out=None):
-    ctx = ctx or default_context()
+def _score(X: NamedMatrix, matG: NamedMatrix, opts_kw: dict, ctx, out=None):
+    """`ctx`: a Context, None (default context of device 0) or a list of Contexts on different devices — the
+    columns are then sharded over them by plaidgpu_score_multi (host buffers only)."""
+    ctxs = list(ctx) if isinstance(ctx, (list, tuple)) else None
+    ctx = (ctxs[0] if ctxs else ctx) or default_context()
     Xm = X.mat
     xr = X.rownames
     if xr is None or matG.rownames is None:
@@ -251,7 +254,8 @@ def _score(X: NamedMatrix, matG: NamedMatrix, opts_kw: dict, ctx: Optional[Conte
     if not (rowmap >= 0).any():  # R/plaid.R:66-69
         _message("[plaid] ERROR. No overlapping features.")
         return None
-    ctx.set_genesets(matG.mat)
+    for cx in (ctxs or [ctx]):
+        cx.set_genesets(matG.mat)
     keep: list = []
     M = _matrix_struct(Xm, keep)
     if M.P != len(xr):
@@ -265,7 +269,11 @@ def _score(X: NamedMatrix, matG: NamedMatrix, opts_kw: dict, ctx: Optional[Conte
         out_loc = L.DEVICE if (_is_torch(out) and out.is_cuda) else L.HOST
         out_ptr = _ptr(out)
     o = _opts(ctx.lib, out_location=out_loc, **opts_kw)
-    rc = ctx.lib.plaidgpu_score(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(o), out_ptr)
+    if ctxs and len(ctxs) > 1:
+        hs = (C.c_void_p * len(ctxs))(*[cx.h for cx in ctxs])
+        rc = ctx.lib.plaidgpu_score_multi(hs, len(ctxs), C.byref(M), rowmap.ctypes.data, C.byref(o), out_ptr)
+    else:
+        rc = ctx.lib.plaidgpu_score(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(o), out_ptr)
     if rc == L.ERR_NOOVERLAP:
         _message("[plaid] ERROR. No overlapping features.")
         return None

@@ -9,7 +9,10 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "common.cuh"
 
@@ -39,6 +42,75 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Blocking memcpy split over a few persistent host threads: moves finished column blocks from the pinned ring
+// into a PAGEABLE caller buffer (what an R caller hands in: Rf_allocMatrix memory) at memory speed, while the
+// next block is still crossing PCIe.
+class CopyPool {
+ public:
+  explicit CopyPool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { run(i); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (bytes < (size_t)(1 << 20) || th_.empty()) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    std::unique_lock<std::mutex> lk(m_);
+    d_ = static_cast<char*>(dst);
+    s_ = static_cast<const char*>(src);
+    n_ = bytes;
+    pending_ = (int)th_.size();
+    ++gen_;
+    cv_work_.notify_all();
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int i) {
+    int seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      const size_t parts = th_.size();
+      const size_t per = ((n_ / parts) + 4095) & ~(size_t)4095;
+      const size_t lo = std::min(n_, per * (size_t)i), hi = std::min(n_, lo + per);
+      char* d = d_;
+      const char* s = s_;
+      lk.unlock();
+      if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+      lk.lock();
+      if (--pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  char* d_ = nullptr;
+  const char* s_ = nullptr;
+  size_t n_ = 0;
+  int gen_ = 0, pending_ = 0;
+  bool stop_ = false;
+};
+
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
 }  // namespace
 
 struct plaidgpu_ctx {
@@ -46,6 +118,12 @@ struct plaidgpu_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_chunk[2] = {};
+  // pageable host output: pinned ring + copy threads (plaidgpu_score_finish)
+  static constexpr int RING = 3;
+  void* ring[RING] = {};
+  size_t ring_bytes = 0;
+  cudaEvent_t ev_ring[RING] = {};
+  CopyPool* pool = nullptr;
   std::string err;
   int64_t launches = 0;
   double ms[4] = {0, 0, 0, 0};  // 0 score, 1 colstats, 2 fixup, 3 rank
@@ -590,6 +668,9 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_ring) if (ev) cudaEventDestroy(ev);
+  for (auto& r : c->ring) if (r) cudaFreeHost(r);
+  delete c->pool;
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -1127,6 +1208,55 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
     CK(cudaStreamSynchronize(c->stream));
   } else {
     // host output: fix up a block of columns, then stream it out while the next block is fixed
+    const bool pageable = N > 0 && is_pageable(out) && !getenv("PLAIDGPU_NO_RING");
+    if (pageable) {
+      // A pageable destination (an R matrix) would make every cudaMemcpyAsync a staged, synchronous copy at a
+      // fraction of the PCIe rate.  Blocks go through a pinned ring instead and the copy threads move block
+      // k - 1 into the caller's matrix while block k crosses PCIe and block k + 1 is fixed up.
+      const size_t want = (size_t)64 << 20;
+      if (!c->ring[0] || c->ring_bytes < want) {
+        for (int i = 0; i < plaidgpu_ctx::RING; ++i) {
+          if (c->ring[i]) cudaFreeHost(c->ring[i]);
+          c->ring[i] = nullptr;
+          CK(cudaMallocHost(&c->ring[i], want));
+          if (!c->ev_ring[i]) CK(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+        }
+        c->ring_bytes = want;
+      }
+      if (!c->pool) {
+        int nt = (int)std::min<unsigned>(8, std::max(2u, std::thread::hardware_concurrency() / 2));
+        if (const char* e = getenv("PLAIDGPU_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+        c->pool = new CopyPool(nt);
+      }
+      const int64_t chunk = std::max<int64_t>(1, (int64_t)(c->ring_bytes / ((size_t)S * 8)));
+      const int64_t nchunks = (N + chunk - 1) / chunk;
+      auto drain = [&](int64_t k) {  // block k: wait for its DMA, then pinned slot -> caller matrix
+        const int64_t j0 = k * chunk, j1 = std::min<int64_t>(N, j0 + chunk);
+        cudaEventSynchronize(c->ev_ring[k % plaidgpu_ctx::RING]);
+        c->pool->copy(out + j0 * S, c->ring[k % plaidgpu_ctx::RING], (size_t)(j1 - j0) * S * sizeof(double));
+      };
+      for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t j0 = k * chunk, j1 = std::min<int64_t>(N, j0 + chunk);
+        if (fix) {
+          CK(launch_fixup(c->raw, c->raw, S, S, j0, j1, med, cc, alpha, beta, c->stream));
+          c->launches += 1;
+        }
+        CK(cudaEventRecord(c->ev_chunk[k & 1], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k & 1], 0));
+        CK(cudaMemcpyAsync(c->ring[k % plaidgpu_ctx::RING], c->raw + j0 * S, (size_t)(j1 - j0) * S * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(c->ev_ring[k % plaidgpu_ctx::RING], c->copy_stream));
+        if (k >= 1) drain(k - 1);
+      }
+      CK(cudaEventRecord(c->ev[5], c->stream));
+      if (nchunks > 0) drain(nchunks - 1);
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaStreamSynchronize(c->copy_stream));
+      float msr = 0.f;
+      cudaEventElapsedTime(&msr, c->ev[4], c->ev[5]);
+      c->ms[2] = msr;
+      return PLAIDGPU_OK;
+    }
     int64_t chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / ((int64_t)S * 8));
     int k = 0;
     for (int64_t j0 = 0; j0 < N; j0 += chunk, ++k) {
@@ -1335,6 +1465,156 @@ int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* row
     if (rc) return fail(c, rc, "combine_medians failed");
   }
   return plaidgpu_score_finish(c, &s, out);
+}
+
+// -----------------------------------------------------------------------------------------
+// Several devices from ONE host process (what an R session has): contiguous column shards, one host thread and
+// one context per device, every shard's block written straight into the caller's S x N matrix, the cross-shard
+// scalars combined on the host in column order (bit-identical to the single-context result).  The axis is the
+// column loop of chunked_crossprod (R/plaid.R:110-119).
+namespace {
+struct ShardBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, count = 0, gen = 0;
+  explicit ShardBarrier(int n_) : n(n_) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const int g = gen;
+    if (++count == n) {
+      count = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+  }
+};
+}  // namespace
+
+int plaidgpu_score_multi(plaidgpu_ctx* const* ctxs, int n, const plaidgpu_matrix* X, const int32_t* rowmap,
+                         const plaidgpu_opts* opts, double* out) {
+  if (!ctxs || n <= 0 || !ctxs[0]) return PLAIDGPU_ERR_ARG;
+  plaidgpu_ctx* c = ctxs[0];
+  if (!X || !rowmap || !opts) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (X->location != PLAIDGPU_HOST || opts->out_location != PLAIDGPU_HOST)
+    return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_multi: X and out must be in host memory");
+  if (n == 1 || X->N < 2 * (int64_t)n) return plaidgpu_score(c, X, rowmap, opts, out);
+  for (int r = 0; r < n; ++r) {
+    if (!ctxs[r] || !ctxs[r]->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_multi: every context needs plaidgpu_set_genesets");
+    if (ctxs[r]->S != c->S) return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_multi: contexts hold different gene sets");
+    for (int q = 0; q < r; ++q)
+      if (ctxs[q] == ctxs[r]) return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_multi: the same context twice");
+  }
+  if (opts->scorer == PLAIDGPU_GSVA && opts->gsva_ecdf == PLAIDGPU_ROWTF_ECDF)
+    return fail(c, PLAIDGPU_ERR_ARG, "plaidgpu_score_multi: gsva rowtf = ecdf ranks across samples (use one context, or the row exchange of plaid_b200/sharded.py)");
+  try {
+    const int64_t N = X->N;
+    const int32_t S = c->S, P = X->P;
+    const bool norm = (opts->scorer == PLAIDGPU_PLAID && opts->normalize) || opts->scorer == PLAIDGPU_SSGSEA ||
+                      opts->scorer == PLAIDGPU_UCELL || opts->scorer == PLAIDGPU_AUCELL || opts->scorer == PLAIDGPU_GSVA;
+    const bool gsva_z = opts->scorer == PLAIDGPU_GSVA && opts->gsva_ecdf == PLAIDGPU_ROWTF_Z && !(opts->row_mean && opts->row_sd);
+    std::vector<int64_t> lo((size_t)n + 1);
+    for (int r = 0; r <= n; ++r) lo[r] = N * r / n;
+    std::vector<std::vector<int32_t>> pbuf((size_t)n);
+    std::vector<plaidgpu_matrix> M((size_t)n, *X);
+    for (int r = 0; r < n; ++r) {
+      M[r].N = lo[r + 1] - lo[r];
+      if (X->kind == PLAIDGPU_CSC) {
+        const int32_t base = X->p[lo[r]];
+        pbuf[r].resize((size_t)M[r].N + 1);
+        for (int64_t j = lo[r]; j <= lo[r + 1]; ++j) pbuf[r][(size_t)(j - lo[r])] = X->p[j] - base;
+        M[r].p = pbuf[r].data();
+        M[r].i = X->i + base;
+        M[r].x = X->x + base;
+      } else {
+        M[r].x = X->x + lo[r] * (int64_t)P;
+      }
+    }
+    std::vector<plaidgpu_scalars> loc((size_t)n);
+    std::vector<int> rc((size_t)n, PLAIDGPU_OK);
+    std::vector<double> med((size_t)std::max<int64_t>(N, 1));
+    std::vector<std::vector<double>> part(gsva_z ? (size_t)n : 0, std::vector<double>((size_t)P));
+    std::vector<double> rmean(gsva_z ? (size_t)P : 0), rsd(gsva_z ? (size_t)P : 0);
+    plaidgpu_scalars g;
+    memset(&g, 0, sizeof(g));
+    ShardBarrier bar(n);
+    auto failed = [&] {
+      for (int r = 0; r < n; ++r)
+        if (rc[r]) return true;
+      return false;
+    };
+    auto body = [&](int r) {
+      plaidgpu_ctx* cr = ctxs[r];
+      plaidgpu_opts o = *opts;
+      if (gsva_z) {  // rowMeans / rowSds over ALL shards, summed in shard order (R/plaid.R:343)
+        rc[r] = plaidgpu_row_moments(cr, &M[r], nullptr, part[r].data());
+        bar.wait();
+        if (failed()) return;
+        if (r == 0)
+          for (int32_t q = 0; q < P; ++q) {
+            double a = 0.0;
+            for (int k = 0; k < n; ++k) a += part[k][q];
+            rmean[q] = a / (double)N;
+          }
+        bar.wait();
+        rc[r] = plaidgpu_row_moments(cr, &M[r], rmean.data(), part[r].data());
+        bar.wait();
+        if (failed()) return;
+        if (r == 0)
+          for (int32_t q = 0; q < P; ++q) {
+            double a = 0.0;
+            for (int k = 0; k < n; ++k) a += part[k][q];
+            rsd[q] = N > 1 ? sqrt(a / (double)(N - 1)) : NAN;
+          }
+        bar.wait();
+        o.row_mean = rmean.data();
+        o.row_sd = rsd.data();
+      }
+      rc[r] = plaidgpu_score_begin(cr, &M[r], rowmap, &o, &loc[r]);
+      bar.wait();
+      if (failed()) return;
+      plaidgpu_scalars s = loc[0];
+      for (int k = 1; k < n; ++k) {
+        s.x_min = fmin(s.x_min, loc[k].x_min);
+        s.x_max = fmax(s.x_max, loc[k].x_max);
+        s.rank_max = fmax(s.rank_max, loc[k].rank_max);
+      }
+      rc[r] = plaidgpu_score_compute(cr, &s, nullptr);
+      loc[r].score_min = s.score_min;
+      bar.wait();
+      if (failed()) return;
+      if (norm) {
+        double smin = INFINITY;
+        for (int k = 0; k < n; ++k) smin = fmin(smin, loc[k].score_min);
+        const int iz = opts->ignore_zero < 0 ? (smin == 0.0 ? 1 : 0) : (opts->ignore_zero != 0);  // R/plaid.R:556-557
+        rc[r] = plaidgpu_get_col_medians_for(cr, iz, med.data() + lo[r]);
+        bar.wait();
+        if (failed()) return;
+        if (r == 0) rc[0] = plaidgpu_combine_medians(iz, smin, med.data(), med.data(), N, &g);
+        bar.wait();
+        if (failed()) return;
+        s.ignore_zero = g.ignore_zero;
+        s.med_mean = g.med_mean;
+        s.score_min = smin;
+      }
+      rc[r] = plaidgpu_score_finish(cr, &s, out + lo[r] * (int64_t)S);
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < n; ++r) th.emplace_back(body, r);
+    body(0);
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; ++r)
+      if (rc[r]) {
+        if (r > 0) c->err = "shard " + std::to_string(r) + ": " + ctxs[r]->err;
+        return rc[r];
+      }
+    return PLAIDGPU_OK;
+  } catch (const std::bad_alloc&) {
+    return fail(c, PLAIDGPU_ERR_NOMEM, "out of host memory");
+  } catch (...) {
+    return fail(c, PLAIDGPU_ERR_ARG, "unexpected failure in plaidgpu_score_multi");
+  }
 }
 
 int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t* rowmap, const double* colscale,

@@ -421,6 +421,45 @@ def test_sharded_protocol_is_shard_count_invariant():
             assert np.array_equal(np.concatenate(outs, axis=1), whole)
 
 
+def test_c_level_multi_context_entry_and_pageable_ring(monkeypatch):
+    """plaidgpu_score_multi (one host thread per context, blocks written straight into the caller's matrix) equals
+    the one-context result bit for bit for 2 and 3 contexts, sparse and dense input, every scorer family; the
+    pageable-destination path (pinned ring + copy threads) equals the direct copy into pinned memory."""
+    import torch
+    P, N, S = 1500, 333, 1800
+    X = synth.sparse_x_numpy(P, N, seed=93)
+    D = synth.dense_x_numpy(P, 97, seed=94)
+    G = synth.genesets_numpy(P, S, seed=95, size_cap=(5, 200))
+    names = synth.gene_names(P)
+    Gn = pb.NamedMatrix(G, names)
+    ctxs = [pb.Context(0) for _ in range(3)]
+    calls = [("plaid", lambda c, M: pb.plaid(M, Gn, ctx=c)), ("plaid raw sum", lambda c, M: pb.plaid(M, Gn, stats="sum", normalize=False, ctx=c)),
+             ("ssgsea", lambda c, M: pb.replaid_ssgsea(M, Gn, ctx=c)), ("ucell", lambda c, M: pb.replaid_ucell(M, Gn, rmax=200, ctx=c)),
+             ("scse", lambda c, M: pb.replaid_scse(M, Gn, ctx=c)), ("gsva", lambda c, M: pb.replaid_gsva(M, Gn, ctx=c))]
+    for label, f in calls:
+        for mat in (X, D):
+            if label == "gsva" and mat is X:
+                continue
+            M = pb.NamedMatrix(mat, names)
+            whole = f(ctxs[0], M).mat
+            for world in (2, 3):
+                got = f(ctxs[:world], M).mat
+                if label == "gsva":  # row sums are added per shard: z agrees to the last bits only
+                    assert rel_err(got, whole) < tol(1e-9), (label, world)
+                else:
+                    assert np.array_equal(got, whole), (label, world)
+    # pageable destination (numpy malloc) vs pinned destination: same bits, several ring blocks (64 MB each)
+    Nbig = 5000
+    Xb = synth.sparse_x_numpy(P, Nbig, seed=96)
+    a = pb.plaid(pb.NamedMatrix(Xb, names), Gn, ctx=ctxs[0]).mat                   # pageable: ring path (72 MB)
+    pinned = torch.empty(S * Nbig, dtype=torch.float64).pin_memory()
+    b = pb.plaid(pb.NamedMatrix(Xb, names), Gn, ctx=ctxs[0], out=pinned.numpy().reshape((S, Nbig), order="F")).mat
+    assert np.array_equal(a, np.asarray(b))
+    monkeypatch.setenv("PLAIDGPU_NO_RING", "1")
+    c2 = pb.plaid(pb.NamedMatrix(Xb, names), Gn, ctx=ctxs[0]).mat
+    assert np.array_equal(a, c2)
+
+
 def test_median_choice_across_shards():
     """normalize_medians uses ONE median, picked by min(x) == 0 over ALL shards (R/plaid.R:556-557); each shard
     computes up front only the median its own minimum predicts and the other one on demand.  Long columns
