@@ -299,6 +299,9 @@ int plaidgpu_plan_info(const plaidgpu_ctx* ctx, int32_t* tile_sets, int32_t* n_t
 /* the tensor-core block of the current plan: rows of X scored by tcgen05 (0 = the pass is off), the same
  * padded to whole K blocks of 128, and the number of 8-bit fixed-point digits per value */
 int plaidgpu_tc_info(const plaidgpu_ctx* ctx, int32_t* block_rows, int32_t* padded_rows, int32_t* slices);
+/* the tail pass of the current plan (sparse X): rows of X outside the block that are in at least one set
+ * (0 = the pass is off and the fp64 scatter pass finishes the scores), cells per gene-major tile */
+int plaidgpu_tail_info(const plaidgpu_ctx* ctx, int32_t* tail_rows, int32_t* tile_cells);
 
 /* ---- expression-matrix files (scope row f4) -------------------------------------------
  * The on-disk formats on the input side of the path, decoded on the host into the CSC arrays of a

@@ -130,9 +130,12 @@ class Context:
                                                C.byref(gk), C.byref(gb)))
         tr, tp, tsl = (C.c_int32() for _ in range(3))
         self.check(self.lib.plaidgpu_tc_info(self.h, C.byref(tr), C.byref(tp), C.byref(tsl)))
+        tlr, tlc = C.c_int32(), C.c_int32()
+        self.check(self.lib.plaidgpu_tail_info(self.h, C.byref(tlr), C.byref(tlc)))
         return {"tile_sets": ts.value, "n_tiles": nt.value, "nnz_mapped": nm.value, "warps_per_cta": wp.value,
                 "ctas": ct.value, "gather_block": gk.value, "gather_blocks": gb.value,
-                "tc_rows": tr.value, "tc_rows_padded": tp.value, "tc_slices": tsl.value}
+                "tc_rows": tr.value, "tc_rows_padded": tp.value, "tc_slices": tsl.value,
+                "tail_rows": tlr.value, "tail_tile_cells": tlc.value}
 
 
 _default_ctx: dict = {}

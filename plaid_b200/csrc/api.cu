@@ -152,6 +152,10 @@ struct plaidgpu_ctx {
   // tensor-core pass over the block (tc_kernels.cu): tcK = block rows padded to a multiple of 128 (0 = off)
   int32_t tcK = 0, tc_rows = 0, tc_slices = 4;
   DevBuf d_abits, b_tcB, b_colinv, b_tcflag;
+  // tail pass over every other row of a sparse X (tail_kernels.cu): Pt rows with a tail id, set-major member lists
+  bool tail_on = false;
+  int32_t Pt = 0;
+  DevBuf d_tmap, d_tptr, d_tidx, d_sorder, b_colfb, b_tcnt, b_trowptr, b_ttotal, b_tecell, b_teq, b_ttmp, b_tcounter;
 
   // current scoring call
   bool in_call = false, computed = false;
@@ -406,6 +410,41 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
         abits[((m * kbn + kb) * 128 + i) * 4 + (b >> 5)] |= 1u << (8 * (t & 3) + (t >> 2));
       }
   }
+  // tail pass (sparse X with a tensor-core block): every other row that is in at least one set gets a tail id
+  // (ascending with the row index = the reference's summation order); member lists per set; sets by tail size
+  std::vector<int32_t> tmap, sorder;
+  std::vector<uint32_t> tptr;
+  std::vector<uint16_t> tidx;
+  int32_t Pt = 0;
+  bool tail_on = !dense && tcK > 0;
+  if (const char* e = getenv("PLAIDGPU_TAIL")) tail_on = tail_on && atoi(e) != 0;
+  if (tail_on) {
+    tmap.assign((size_t)P, -1);
+    for (int32_t r = 0; r < P; ++r)
+      if (deg[r] > 0 && local_of_row[r] < 0) tmap[r] = Pt++;
+    if (Pt > 65535) tail_on = false;  // 16-bit member ids
+  }
+  if (tail_on) {
+    tptr.assign((size_t)S + 1, 0);
+    tidx.reserve((size_t)nnzm);
+    std::vector<uint16_t> one;
+    for (int32_t s = 0; s < S; ++s) {
+      one.clear();
+      for (int32_t q = c->Gp[s]; q < c->Gp[s + 1]; ++q) {
+        const int32_t r = g2x[c->Gi[q]];
+        if (r >= 0 && tmap[r] >= 0) one.push_back((uint16_t)tmap[r]);
+      }
+      std::sort(one.begin(), one.end());
+      tidx.insert(tidx.end(), one.begin(), one.end());
+      tptr[s + 1] = (uint32_t)tidx.size();
+    }
+    if (tidx.empty()) tidx.push_back(0);
+    sorder.resize((size_t)S);
+    for (int32_t s = 0; s < S; ++s) sorder[s] = s;
+    std::stable_sort(sorder.begin(), sorder.end(), [&](int32_t a, int32_t b) {
+      return tptr[a + 1] - tptr[a] > tptr[b + 1] - tptr[b];
+    });
+  }
   std::vector<double> inv_mean((size_t)S), inv_one((size_t)S, 1.0);
   for (int32_t s = 0; s < S; ++s) inv_mean[s] = 1.0 / (1e-8 + ns[s]);  // R/plaid.R:75-76
 
@@ -423,7 +462,13 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
   CK(up(c->d_dptr, dptr.data(), dptr.size() * sizeof(uint32_t)));
   CK(up(c->d_didx, didx.data(), didx.size() * sizeof(uint32_t)));
   CK(up(c->d_abits, abits.data(), abits.size() * sizeof(uint32_t)));
+  CK(up(c->d_tmap, tmap.data(), tmap.size() * sizeof(int32_t)));
+  CK(up(c->d_tptr, tptr.data(), tptr.size() * sizeof(uint32_t)));
+  CK(up(c->d_tidx, tidx.data(), tidx.size() * sizeof(uint16_t)));
+  CK(up(c->d_sorder, sorder.data(), sorder.size() * sizeof(int32_t)));
   CK(cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
+  c->tail_on = tail_on;
+  c->Pt = Pt;
   c->Ts = Ts;
   c->T = T;
   c->gK = gK;
@@ -663,7 +708,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
-                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->d_abits, &c->b_tcB, &c->b_colinv, &c->b_tcflag, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
+                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->d_abits, &c->b_tcB, &c->b_colinv, &c->b_tcflag, &c->d_tmap, &c->d_tptr, &c->d_tidx, &c->d_sorder, &c->b_colfb, &c->b_tcnt, &c->b_trowptr, &c->b_ttotal, &c->b_tecell, &c->b_teq, &c->b_ttmp, &c->b_tcounter, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
                     &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list, &c->b_ci, &c->b_cx, &c->b_ce};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -702,6 +747,13 @@ int plaidgpu_tc_info(const plaidgpu_ctx* c, int32_t* block_rows, int32_t* padded
   if (block_rows) *block_rows = c->tcK > 0 ? c->tc_rows : 0;
   if (padded_rows) *padded_rows = c->tcK;
   if (slices) *slices = c->tc_slices;
+  return PLAIDGPU_OK;
+}
+
+int plaidgpu_tail_info(const plaidgpu_ctx* c, int32_t* tail_rows, int32_t* tile_cells) {
+  if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
+  if (tail_rows) *tail_rows = c->tail_on ? c->Pt : 0;
+  if (tile_cells) *tile_cells = tail_tile_cells();
   return PLAIDGPU_OK;
 }
 
@@ -992,26 +1044,63 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     CK(c->b_tcflag.reserve(sizeof(int)));
     CK(cudaMemsetAsync(c->b_tcflag.p, 0, sizeof(int), c->stream));
     CK(c->b_colinv.reserve((size_t)c->N * sizeof(double)));
-    // column chunks keep the digit-row operand within ~4 GiB whatever N is
+    // column chunks keep the digit-row operand within ~4 GiB whatever N is; with a tail pass a chunk is a whole
+    // number of tail tiles and its int64 tail sums (S x chunk) stay within ~4 GB too
+    const bool tail = c->tail_on && !c->dense;
+    const int TC_ = tail_tile_cells();
     int64_t chunk = std::max<int64_t>(ct, ((int64_t)(4ll << 30) / ((int64_t)c->tcK * sl)) / ct * ct);
-    if (chunk > c->N) chunk = c->N;
+    if (tail) {
+      int64_t tiles = std::max<int64_t>(1, (int64_t)(4ll << 30) / ((int64_t)c->S * TC_ * 8));
+      if (const char* e = getenv("PLAIDGPU_TAIL_TILES")) tiles = std::max(1, atoi(e));
+      chunk = std::max<int64_t>(TC_, std::min<int64_t>(chunk / TC_, tiles) * TC_);
+      if (chunk > c->N) chunk = (c->N + TC_ - 1) / TC_ * TC_;
+    } else if (chunk > c->N) {
+      chunk = c->N;
+    }
     CK(c->b_tcB.reserve(tc_operand_bytes(chunk, c->tcK, sl)));
     if (!c->dense && c->nnz > 0) {
       CK(c->b_ci.reserve((size_t)c->nnz * sizeof(int32_t)));
       CK(c->b_cx.reserve((size_t)c->nnz * sizeof(double)));
       CK(c->b_ce.reserve((size_t)c->N * sizeof(int32_t)));
     }
+    const int64_t ctiles = tail ? chunk / TC_ : 0;
+    if (tail) {
+      CK(c->b_tcnt.reserve((size_t)ctiles * c->Pt * sizeof(uint32_t) + 16));
+      CK(c->b_trowptr.reserve((size_t)ctiles * (c->Pt + 1) * sizeof(uint32_t)));
+      CK(c->b_ttotal.reserve((size_t)ctiles * sizeof(uint32_t)));
+      CK(c->b_tecell.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(uint16_t)));
+      CK(c->b_teq.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(int32_t)));
+      CK(c->b_ttmp.reserve((size_t)c->S * (size_t)chunk * sizeof(long long)));
+      CK(c->b_tcounter.reserve(sizeof(unsigned int)));
+      CK(c->b_colfb.reserve((size_t)c->N * sizeof(double)));
+    }
     tc_flag = c->b_tcflag.as<int>();
     for (int64_t j0 = 0; j0 < c->N; j0 += chunk) {
       const int64_t nj = std::min<int64_t>(chunk, c->N - j0);
+      const int tiles = tail ? (int)((nj + TC_ - 1) / TC_) : 0;
       if (c->dense) {
         CK(launch_tc_prep_dense(p.xx + j0 * (int64_t)c->P, c->P, nj, p.mode, p.a0, p.a1, c->tcK, sl,
                                 c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0, c->b_tcflag.as<int>(), c->stream));
       } else {
+        if (tail) CK(cudaMemsetAsync(c->b_tcnt.p, 0, (size_t)tiles * c->Pt * sizeof(uint32_t), c->stream));
         CK(launch_tc_prep_csc(c->xp + j0, c->xi, p.xx, p.r0 ? p.r0 + j0 : nullptr, c->d_dmap.as<uint16_t>(), nj, p.mode,
                               p.a0, p.a1, c->tcK, sl, c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0,
                               c->b_ci.as<int32_t>(), c->b_cx.as<double>(), c->b_ce.as<int32_t>() + j0,
-                              c->b_tcflag.as<int>(), c->stream));
+                              c->b_tcflag.as<int>(), tail ? c->d_tmap.as<int32_t>() : nullptr, c->b_tcnt.as<uint32_t>(),
+                              c->Pt, TC_, tail ? c->b_colfb.as<double>() + j0 : nullptr, c->stream));
+      }
+      if (tail) {
+        // regroup the tail entries of the chunk gene-major per cell tile, then one warp per (tile, set)
+        CK(launch_tile_scan(c->b_tcnt.as<uint32_t>(), c->Pt, tiles, c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(), c->stream));
+        CK(launch_tile_place(c->xp + j0, c->b_ce.as<int32_t>() + j0, c->b_ci.as<int32_t>(), c->b_cx.as<double>(),
+                             p.r0 ? p.r0 + j0 : nullptr, c->d_tmap.as<int32_t>(), c->b_colinv.as<double>() + j0, nj, p.mode,
+                             p.a0, p.a1, c->Pt, c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(),
+                             c->b_tcnt.as<uint32_t>(), c->b_tecell.as<uint16_t>(), c->b_teq.as<int32_t>(), tc_flag, c->stream));
+        CK(launch_tail(c->d_tptr.as<uint32_t>(), c->d_tidx.as<uint16_t>(), c->d_sorder.as<int32_t>(),
+                       c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(), c->b_tecell.as<uint16_t>(),
+                       c->b_teq.as<int32_t>(), c->S, c->Pt, tiles, c->b_ttmp.as<long long>(),
+                       c->b_tcounter.as<unsigned int>(), tc_flag, c->stream));
+        c->launches += 3;
       }
       TcParams t{};
       t.abits = c->d_abits.as<uint4>();
@@ -1019,7 +1108,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       t.N = nj;
       t.colinv = c->b_colinv.as<double>() + j0;
       t.skip_if = tc_flag;
-      t.final = c->dense ? 1 : 0;
+      t.final = (c->dense || tail) ? 1 : 0;
       t.mode = p.mode;
       t.a0 = p.a0;
       t.a1 = p.a1;
@@ -1030,6 +1119,9 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       t.out = c->raw + j0 * (int64_t)c->S;
       t.ld = c->S;
       t.smin = smin;
+      t.tail = tail ? c->b_ttmp.as<long long>() : nullptr;
+      t.tail_ld = (int64_t)tiles * TC_;
+      t.colfb = (tail && p.mode >= XF_SING) ? c->b_colfb.as<double>() + j0 : nullptr;
       CK(launch_tc_score(t, c->b_tcB.as<signed char>(), c->tcK, sl, c->stream));
       c->launches += 2;
     }
@@ -1084,6 +1176,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       p.xx = c->b_cx.as<double>();
       p.xe = c->b_ce.as<int32_t>();
     }
+    p.run_if = (use_tc && c->tail_on) ? tc_flag : nullptr;  // with a tail pass the scatter pass is the fallback only
     CK(launch_score(p, false, c->cfg, c->stream));
     c->launches += 1;
   }

@@ -56,6 +56,7 @@ struct ScoreParams {
   // optional: order-preserving key (key_of) of the smallest FINAL score written, atomicMin'ed per warp;
   // tells the host which median normalize_medians will need before the statistics pass runs
   unsigned long long* smin;
+  const int* run_if;  // optional device flag: the kernel runs only when it is non-zero (fallback after a fixed-point pass)
 };
 
 // Gather pass over one block of K genes (the dense-ish part of the product):
@@ -109,6 +110,12 @@ struct TcParams {
   double* out;
   int64_t ld;
   unsigned long long* smin;
+  // optional (sparse X): int64 fixed-point sums of the rows outside the block, [S][tail_ld] (tail_kernels.cu),
+  // added to the block's integer sums before the conversion to fp64; column 0 = the first column of this launch
+  const long long* tail;
+  int64_t tail_ld;
+  const double* colfb;   // [N] f(rank of the zero group) per column (rank scorers on sparse X), or nullptr
+  int32_t dbg;           // development switches (PLAIDGPU_TC_DBG): 1 no tail loads, 2 no wait for A, 4 no wait for B
 };
 
 struct LaunchCfg {
@@ -138,10 +145,21 @@ size_t tc_operand_bytes(int64_t N, int Kp, int slices);  // bytes of the digit-r
 cudaError_t launch_tc_prep_csc(const int32_t* xp, const int32_t* xi, const double* xx, const double* r0,
                                const uint16_t* dmap, int64_t N, int mode, double a0, double a1, int Kp, int slices,
                                signed char* Bd, double* colinv, int32_t* oi, double* ox, int32_t* xe, int* flag,
-                               cudaStream_t st);
+                               const int32_t* tmap, uint32_t* tcnt, int32_t Pt, int tileC, double* colfb, cudaStream_t st);
 cudaError_t launch_tc_prep_dense(const double* x, int32_t P, int64_t N, int mode, double a0, double a1, int Kp,
                                  int slices, signed char* Bd, double* colinv, int* flag, cudaStream_t st);
 cudaError_t launch_tc_score(const TcParams& p, const signed char* Bd, int Kp, int slices, cudaStream_t st);
+
+// tail_kernels.cu — rows of a sparse X outside the tensor-core block: gene-major cell tiles, one warp per (tile, set)
+int tail_tile_cells();
+cudaError_t launch_tile_scan(uint32_t* cnt, int32_t Pt, int tiles, uint32_t* rowptr, uint32_t* total, cudaStream_t st);
+cudaError_t launch_tile_place(const int32_t* xp, const int32_t* xe, const int32_t* oi, const double* ox, const double* r0,
+                              const int32_t* tmap, const double* colinv, int64_t N, int mode, double a0, double a1,
+                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint16_t* ecell,
+                              int32_t* eq, const int* skip_if, cudaStream_t st);
+cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_t* sorder, const uint32_t* rowptr,
+                        const uint32_t* total, const uint16_t* ecell, const int32_t* eq, int32_t S, int32_t Pt, int tiles,
+                        long long* tmp, unsigned int* counter, const int* skip_if, cudaStream_t st);
 
 // stats_kernels.cu
 // per-column statistics of a dense S x N matrix (ld = leading dimension):

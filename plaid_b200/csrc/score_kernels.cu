@@ -46,6 +46,7 @@ __device__ __forceinline__ void ld_rec32(const void* p, unsigned long long& a, u
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(768, 1) k_scatter(const ScoreParams p) {
+  if (p.run_if && *p.run_if == 0) return;
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;

@@ -1,0 +1,283 @@
+// K3 — the sparse remainder of the gene-set score product (reference R/plaid.R:100-123, Matrix::crossprod ->
+// CHOLMOD): every row of a sparse X that is NOT in the tensor-core block (tc_kernels.cu), i.e. the many genes
+// that are expressed in a few per cent of the cells and sit in ~100 sets each.
+//
+// Formulation (replaces the lanes = genes scatter of score_kernels.cu on the fixed-point path):
+//   * the cells are cut into tiles of TAIL_C columns; per tile the tail entries of X are regrouped GENE-major
+//     (k_tile_scan / k_tile_place: counting sort by tail row -> `rowptr`, `ecell` (cell inside the tile, u16) and
+//     `eq` (the value in the column's fixed point, the same 2^e_j the tensor-core pass uses, int32));
+//   * one warp owns one (tile, set) item at a time: it walks the set's tail members and adds each member's
+//     sparse row of the tile into TAIL_C accumulators in shared memory, LANES = the row's ENTRIES.  The cells
+//     of one row are distinct, and rows are handled one after the other, so there are no duplicate addresses
+//     inside a step: no tags, no retries, no atomics — a step is one 32-bit LDS / IADD / STS per lane;
+//   * accumulators are 64-bit integers split into a u32 low word (touched by every add) and an i16 high word
+//     (touched only on carry / borrow): random 32-bit accesses cost ~3 shared-memory wavefronts per warp
+//     instead of the ~6 of a 64-bit access, and integer sums are exact and order-independent;
+//   * the finished row (TAIL_C sums of one set) is written as int64 to `tmp[set][cell]` with coalesced stores;
+//     the tensor-core kernel fetches its 128 sets x 48 cells by TMA and adds it to its own integer sums
+//     before the one conversion to fp64 (so tail + block is exact, then scaled by 2^-e_j).
+// Items are dealt dynamically (one atomic per item) in decreasing order of the set's tail size.
+#include "common.cuh"
+
+namespace plaidgpu {
+
+namespace {
+
+constexpr int TAIL_WARPS = 32;
+
+// block-wide exclusive scan of the per-(tile, tail row) entry counts -> tile-local row pointers; the counters
+// are zeroed again (k_tile_place re-uses them as cursors).  grid = tiles, 1024 threads.
+__global__ void __launch_bounds__(1024) k_tile_scan(uint32_t* __restrict__ cnt, int32_t Pt, uint32_t* __restrict__ rowptr,
+                                                    uint32_t* __restrict__ total) {
+  __shared__ uint32_t wsum[32];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t* __restrict__ c = cnt + (size_t)t * Pt;
+  uint32_t* __restrict__ rp = rowptr + (size_t)t * (Pt + 1);
+  const int per = (Pt + 1023) / 1024;
+  const int lo = min(Pt, tid * per), hi = min(Pt, lo + per);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = wsum[lane], a = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(FULL, a, o);
+      if (lane >= o) a += u;
+    }
+    wsum[lane] = a - v;  // exclusive
+    if (lane == 31) {
+      total[t] = a;
+      rp[Pt] = a;
+    }
+  }
+  __syncthreads();
+  uint32_t run = wsum[w] + incl - s;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t v = c[i];
+    rp[i] = run;
+    run += v;
+    c[i] = 0;
+  }
+}
+
+// one warp per column: tail entries of the (compacted) column -> their slot in the tile's gene-major arrays
+__global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ xp, const int32_t* __restrict__ xe,
+                                                    const int32_t* __restrict__ oi, const double* __restrict__ ox,
+                                                    const double* __restrict__ r0, const int32_t* __restrict__ tmap,
+                                                    const double* __restrict__ colinv, int64_t N, int mode, double a0,
+                                                    double a1, int32_t Pt, int C, const uint32_t* __restrict__ rowptr,
+                                                    const uint32_t* __restrict__ total, uint32_t* __restrict__ cnt,
+                                                    uint16_t* __restrict__ ecell, int32_t* __restrict__ eq,
+                                                    const int* __restrict__ skip_if) {
+  if (skip_if && *skip_if != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = w0; j < N; j += nw) {
+    const int t = (int)(j / C);
+    const uint32_t cell = (uint32_t)(j - (int64_t)t * C);
+    uint32_t base = 0;  // entries of the tiles before this one
+    for (int u = lane; u < t; u += 32) base += total[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(FULL, base, o);
+    const uint32_t* __restrict__ rp = rowptr + (size_t)t * (Pt + 1);
+    uint32_t* __restrict__ cur = cnt + (size_t)t * Pt;
+    double fb = 0.0;
+    if (mode >= XF_SING) fb = xform_value(mode, r0 ? r0[j] : 0.0, a0, a1);
+    const double sc = 1.0 / colinv[j];  // 2^e_j, exact
+    for (int32_t e = xp[j] + lane; e < xe[j]; e += 32) {
+      const int32_t g = tmap[oi[e]];
+      if (g < 0) continue;
+      double v = xform_value(mode, ox[e], a0, a1);
+      if (mode >= XF_SING) v -= fb;
+      const uint32_t pos = base + rp[g] + atomicAdd(cur + g, 1u);
+      ecell[pos] = (uint16_t)cell;
+      eq[pos] = (int32_t)__double2ll_rn(v * sc);
+    }
+  }
+}
+
+struct TailParams {
+  const uint32_t* tptr;    // [S + 1] set -> its tail members
+  const uint16_t* tidx;    // tail ids, ascending inside a set
+  const int32_t* sorder;   // [S] sets in decreasing order of their tail size
+  const uint32_t* rowptr;  // [tiles][Pt + 1]
+  const uint32_t* total;   // [tiles]
+  const uint16_t* ecell;
+  const int32_t* eq;
+  int32_t S, Pt, C, tiles;
+  long long* tmp;          // [S][ld] int64 sums
+  int64_t ld;              // = tiles * C
+  unsigned int* counter;   // work counter (zeroed before the launch)
+  const int* skip_if;
+};
+
+__global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p) {
+  if (p.skip_if && *p.skip_if != 0) return;
+  extern __shared__ uint32_t tail_sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int C = p.C;
+  uint32_t* __restrict__ lo = tail_sm + (size_t)w * C;
+  short* __restrict__ hi = reinterpret_cast<short*>(tail_sm + (size_t)TAIL_WARPS * C) + (size_t)w * C;
+  for (int c = lane; c < C; c += 32) {
+    lo[c] = 0u;
+    hi[c] = 0;
+  }
+  __syncwarp();
+  const unsigned nitems = (unsigned)p.tiles * (unsigned)p.S;
+  for (;;) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(p.counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= nitems) break;
+    const int t = (int)(item / (unsigned)p.S);
+    const int s = p.sorder[item - (unsigned)t * (unsigned)p.S];
+    const uint32_t* __restrict__ rp = p.rowptr + (size_t)t * (p.Pt + 1);
+    uint32_t base = 0;
+    for (int u = lane; u < t; u += 32) base += p.total[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(FULL, base, o);
+    const uint16_t* __restrict__ ec = p.ecell + base;
+    const int32_t* __restrict__ eqv = p.eq + base;
+    const uint32_t m0 = p.tptr[s], m1 = p.tptr[s + 1];
+    for (uint32_t mb = m0; mb < m1; mb += 32) {
+      // lane i looks up the row of member mb + i in this tile
+      uint32_t r0 = 0, rn = 0;
+      if (mb + lane < m1) {
+        const uint32_t g = p.tidx[mb + lane];
+        r0 = rp[g];
+        rn = rp[g + 1] - r0;
+      }
+      const int cnt = (int)min(32u, m1 - mb);
+      // software pipeline over the (member, 32-entry segment) sequence: four segments are in flight (their entries
+      // come from L2, ~300 clocks away), added in fetch order
+      int fk = 0;          // fetch cursor: member
+      uint32_t foff = 0;   //               offset inside its row
+      auto fetch = [&](uint32_t& cc, int32_t& qq) -> bool {
+        uint32_t nk = 0;
+        while (fk < cnt) {
+          nk = __shfl_sync(FULL, rn, fk);
+          if (foff < nk) break;
+          ++fk;
+          foff = 0;
+        }
+        cc = 0xFFFFu;
+        qq = 0;
+        if (fk >= cnt) return false;
+        const uint32_t pk = __shfl_sync(FULL, r0, fk);
+        const uint32_t i = foff + (uint32_t)lane;
+        if (i < nk) {
+          cc = ec[pk + i];
+          qq = eqv[pk + i];
+        }
+        foff += 32;
+        return true;
+      };
+      auto add = [&](uint32_t c, int32_t q) {
+        if (c != 0xFFFFu) {
+          const uint32_t uq = (uint32_t)q;
+          const uint32_t nv = lo[c] + uq;
+          lo[c] = nv;
+          const int d = (nv < uq ? 1 : 0) - (q < 0 ? 1 : 0);  // carry out of / borrow from the low word
+          if (d != 0) hi[c] = (short)(hi[c] + d);
+        }
+        __syncwarp();
+      };
+      uint32_t c0, c1, c2, c3;
+      int32_t q0, q1, q2, q3;
+      bool ok0 = fetch(c0, q0);
+      bool ok1 = ok0 && fetch(c1, q1);
+      bool ok2 = ok1 && fetch(c2, q2);
+      bool ok3 = ok2 && fetch(c3, q3);
+      for (;;) {
+        if (!ok0) break;
+        add(c0, q0);
+        ok0 = ok3 && fetch(c0, q0);
+        if (!ok1) break;
+        add(c1, q1);
+        ok1 = ok0 && fetch(c1, q1);
+        if (!ok2) break;
+        add(c2, q2);
+        ok2 = ok1 && fetch(c2, q2);
+        if (!ok3) break;
+        add(c3, q3);
+        ok3 = ok2 && fetch(c3, q3);
+      }
+    }
+    // flush: int64 sums of set s over the tile's cells, coalesced; re-zero
+    long long* __restrict__ o = p.tmp + (size_t)s * p.ld + (size_t)t * C;
+    for (int c = lane; c < C; c += 32) {
+      const long long v = ((long long)hi[c] << 32) | (long long)lo[c];
+      lo[c] = 0u;
+      hi[c] = 0;
+      __stcs(o + c, v);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+int tail_tile_cells() { return 1056; }  // 22 tensor-core cell tiles of 48
+
+size_t tail_smem_bytes() { return (size_t)TAIL_WARPS * tail_tile_cells() * 6; }
+
+cudaError_t launch_tile_scan(uint32_t* cnt, int32_t Pt, int tiles, uint32_t* rowptr, uint32_t* total, cudaStream_t st) {
+  if (tiles <= 0) return cudaSuccess;
+  k_tile_scan<<<(unsigned)tiles, 1024, 0, st>>>(cnt, Pt, rowptr, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_place(const int32_t* xp, const int32_t* xe, const int32_t* oi, const double* ox, const double* r0,
+                              const int32_t* tmap, const double* colinv, int64_t N, int mode, double a0, double a1,
+                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint16_t* ecell,
+                              int32_t* eq, const int* skip_if, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t grid = (N + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_tile_place<<<(unsigned)grid, 256, 0, st>>>(xp, xe, oi, ox, r0, tmap, colinv, N, mode, a0, a1, Pt, tail_tile_cells(),
+                                               rowptr, total, cnt, ecell, eq, skip_if);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_t* sorder, const uint32_t* rowptr,
+                        const uint32_t* total, const uint16_t* ecell, const int32_t* eq, int32_t S, int32_t Pt, int tiles,
+                        long long* tmp, unsigned int* counter, const int* skip_if, cudaStream_t st) {
+  if (tiles <= 0 || S <= 0) return cudaSuccess;
+  TailParams p{};
+  p.tptr = tptr;
+  p.tidx = tidx;
+  p.sorder = sorder;
+  p.rowptr = rowptr;
+  p.total = total;
+  p.ecell = ecell;
+  p.eq = eq;
+  p.S = S;
+  p.Pt = Pt;
+  p.C = tail_tile_cells();
+  p.tiles = tiles;
+  p.tmp = tmp;
+  p.ld = (int64_t)tiles * p.C;
+  p.counter = counter;
+  p.skip_if = skip_if;
+  const size_t smem = tail_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  k_tail<<<(unsigned)sms, TAIL_WARPS * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace plaidgpu

@@ -40,15 +40,19 @@ namespace {
 constexpr int TC_M = 128;            // sets per CTA tile (TMEM lanes)
 constexpr int TC_N = 192;            // accumulator columns per tile = cells x slices
 constexpr int TC_KB = 128;           // genes (= bytes of a B row) per K block; one swizzle-128B row
-constexpr int TC_BST = 8;            // B ring stages (shared memory)
+constexpr int TC_BST = 5;            // B ring stages (shared memory)
+constexpr int TC_TBOX = 16 * TC_M * 8;  // one tail box: 128 sets x 16 cells of int64 (128-byte swizzled rows)
+constexpr int TC_TBUF = 3 * TC_TBOX;    // tail sums of one accumulator tile (48 cells), double buffered
 constexpr int TC_AST = 4;            // A ring stages (tensor memory, 32 columns each)
 constexpr int TC_ACOL = 2 * TC_N;    // first TMEM column of the A ring
 constexpr int TC_BSTAGE = TC_N * TC_KB;  // 24,576 bytes
 #ifndef TC_EXP_GROUPS
 #define TC_EXP_GROUPS 1              // expander groups of four warps (group g widens K blocks g, g + GROUPS, ...)
 #endif
-constexpr int TC_W_TMA = 4 + 4 * TC_EXP_GROUPS, TC_W_MMA = TC_W_TMA + 1;
-constexpr int TC_THREADS = 32 * (TC_W_MMA + 1);
+constexpr int TC_EPI_WARPS = 8;      // epilogue warps: two per TMEM lane quarter, alternate 32-column chunks
+constexpr int TC_W_TMA = TC_EPI_WARPS + 4 * TC_EXP_GROUPS, TC_W_MMA = TC_W_TMA + 1;
+constexpr int TC_W_TAIL = TC_W_MMA + 1;  // second TMA producer: the tail boxes (waits on the epilogue, so it must not hold up the B ring)
+constexpr int TC_THREADS = 32 * (TC_W_TAIL + 1);
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,18 +142,21 @@ __device__ __forceinline__ uint64_t b_desc(uint32_t saddr) {
 constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 struct TcSmem {
-  unsigned long long b_full[TC_BST], b_empty[TC_BST], a_full[TC_AST], a_empty[TC_AST], acc_full[2], acc_empty[2];
+  unsigned long long b_full[TC_BST], b_empty[TC_BST], a_full[TC_AST], a_empty[TC_AST], acc_full[2], acc_empty[2], tail_full[2], tail_empty[2];
   uint32_t tmem_base;
 };
 
 template <int SLICES>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constant__ CUtensorMap tmapB,
+                                                            const __grid_constant__ CUtensorMap tmapT, const TcParams p) {
   constexpr int CT = TC_N / SLICES;  // cells per tile
   if (p.skip_if && *p.skip_if != 0) return;  // non-finite block entries: the fp64 gather passes run instead
   extern __shared__ uint8_t tc_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = base;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)TC_BST * TC_BSTAGE);
+  uint8_t* sT = base + (size_t)TC_BST * TC_BSTAGE;  // tail boxes (1024-byte aligned: the stage size is a multiple)
+  TcSmem* sm = reinterpret_cast<TcSmem*>(sT + 2 * TC_TBUF);
+  const bool has_tail = p.tail != 0 && !(p.dbg & 1);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
   if (tid == TC_W_MMA * 32) {
@@ -163,7 +170,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
-      mbar_init(smem_u32(&sm->acc_empty[i]), 4);
+      mbar_init(smem_u32(&sm->acc_empty[i]), TC_EPI_WARPS);
+      mbar_init(smem_u32(&sm->tail_full[i]), 1);
+      mbar_init(smem_u32(&sm->tail_empty[i]), TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
   if (w == TC_W_TMA) {
     // ===== TMA producer: B tiles (192 rows x 128 bytes) of cell tile ct, K block kb =====
     uint32_t st = 0, ph = 0;
-    for (int ct = ct0; ct < ct1; ++ct)
+    for (int ct = ct0; ct < ct1; ++ct) {
       for (int kb = 0; kb < KBN; ++kb) {
         mbar_wait(smem_u32(&sm->b_empty[st]), ph ^ 1);
         if (elect_one()) {
@@ -193,6 +202,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
         }
         __syncwarp();
         if (++st == TC_BST) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (w == TC_W_TAIL) {
+    // ===== second TMA producer: the tail sums (tail_kernels.cu) of each tile's 128 sets x 48 cells, three boxes of
+    // 16 cells, double buffered against the epilogue =====
+    if (has_tail)
+      for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
+        const uint32_t tb = t & 1;
+        mbar_wait(smem_u32(&sm->tail_empty[tb]), ((t >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&sm->tail_full[tb]), TC_TBUF);
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            tma_load_2d(smem_u32(sT + (size_t)tb * TC_TBUF + (size_t)b * TC_TBOX), &tmapT, ct * 48 + b * 16, m * TC_M,
+                        smem_u32(&sm->tail_full[tb]));
+        }
+        __syncwarp();
       }
   } else if (w == TC_W_MMA) {
     // ===== MMA issuer: the whole warp walks the barriers, one elected lane issues (elect.sync keeps the
@@ -206,8 +232,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       tc_fence_after();
       const uint32_t dcol = tmem + as * TC_N;
       for (int kb = 0; kb < KBN; ++kb) {
-        mbar_wait(smem_u32(&sm->a_full[sa]), pa);
-        mbar_wait(smem_u32(&sm->b_full[sb]), pb);
+        if (!(p.dbg & 2)) mbar_wait(smem_u32(&sm->a_full[sa]), pa);
+        if (!(p.dbg & 4)) mbar_wait(smem_u32(&sm->b_full[sb]), pb);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t bd = bd0 + (uint64_t)(sb * (TC_BSTAGE >> 4));
@@ -225,10 +251,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       if (elect_one()) tc_commit(smem_u32(&sm->acc_full[as]));
       __syncwarp();
     }
-  } else if (w >= 4 && w < TC_W_TMA) {
+  } else if (w >= TC_EPI_WARPS && w < TC_W_TMA) {
     // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, one K block (32 columns) per stage =====
     // group g (warps 4-7 / 8-11) widens the K blocks q = g, g + 2, ... of this CTA's (cell tile, K block) sequence
-    const int grp = (w - 4) >> 2, wq = (w - 4) & 3;
+    const int grp = (w - TC_EPI_WARPS) >> 2, wq = (w - TC_EPI_WARPS) & 3;
     const int row = wq * 32 + lane;
     const uint4* __restrict__ ab = p.abits + (size_t)m * KBN * TC_M + row;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -256,61 +282,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     }
   } else {
     // ===== epilogue: TMEM -> registers -> fp64 partial set sums (or final scores) -> global =====
-    const int s = m * TC_M + w * 32 + lane;
+    // Warps q and q + 4 share TMEM lane quarter q (set rows 32q .. 32q + 31) and take alternate 32-column chunks.
+    // One warp per scheduler cannot hide its own latencies, so the per-cell instruction count is what sets the
+    // pace: tiles with every cell and every row valid take a predicate-free path.
+    const int wq = w & 3, wh = w >> 2;
+    const int s = m * TC_M + wq * 32 + lane;
     const bool srow = s < p.S;
-    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    const bool rows_full = m * TC_M + wq * 32 + 31 < p.S;  // warp-uniform
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     double inv = 1.0, nsv = 0.0;
     if (p.final && srow) {
       inv = p.inv[s];
       nsv = p.ns[s];
     }
+    const bool rankmode = p.final && p.mode >= XF_SING;
     double vmin = INFINITY;
+    constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
+    const uint32_t tsw = (uint32_t)(lane & 7);
     for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
       const uint32_t as = t & 1, pacc = (t >> 1) & 1;
       mbar_wait(smem_u32(&sm->acc_full[as]), pacc);
       tc_fence_after();
+      if (has_tail) mbar_wait(smem_u32(&sm->tail_full[as]), pacc);
       const int64_t j0 = (int64_t)ct * CT;
       const bool full = j0 + CT <= p.N;  // warp-uniform: only the last cell tile is ragged
       double* __restrict__ optr = p.out + j0 * p.ld + s;
-      const double* __restrict__ civ = p.colinv + j0;
+      // this thread's row of the tail boxes: 128-byte rows, 16-byte chunks XOR-swizzled with (row mod 8)
+      const uint32_t trow = smem_u32(sT) + as * TC_TBUF + (uint32_t)(wq * 32 + lane) * 128u;
 #pragma unroll 1
-      for (int ch = 0; ch < TC_N / 32; ++ch) {
+      for (int ch = wh; ch < ((p.dbg & 16) ? 0 : TC_N / 32); ch += 2) {
         uint32_t v[32];
         tc_ld32(tmem + lane_base + as * TC_N + ch * 32, v);
-        constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
-        double ci[CPC];
+        double ci[CPC], fb[CPC], cs[CPC];
+        long long tl[CPC];
+        const int64_t jc = j0 + ch * CPC;
 #pragma unroll
         for (int c = 0; c < CPC; ++c) {
-          const int cell = ch * CPC + c;
-          ci[c] = (full || j0 + cell < p.N) ? __ldg(civ + cell) : 0.0;
+          const bool okc = full || jc + c < p.N;
+          ci[c] = okc ? __ldg(p.colinv + jc + c) : 0.0;
+          fb[c] = (rankmode && okc) ? (p.colfb ? __ldg(p.colfb + jc + c) : xform_value(p.mode, p.r0 ? p.r0[jc + c] : 0.0, p.a0, p.a1)) : 0.0;
+          cs[c] = (p.final && p.colscale && okc) ? __ldg(p.colscale + jc + c) : 1.0;
+          tl[c] = 0;
+        }
+        if (SLICES == 4 && has_tail) {
+#pragma unroll
+          for (int c = 0; c < CPC; c += 2) {
+            const int cell = ch * CPC + c;  // even: cells c, c + 1 share one 16-byte chunk
+            const uint32_t a = trow + (uint32_t)(cell >> 4) * TC_TBOX + ((((uint32_t)(cell & 15) >> 1) ^ tsw) << 4);
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(tl[c]), "=l"(tl[c + 1]) : "r"(a));
+          }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double val[CPC];
 #pragma unroll
         for (int c = 0; c < CPC; ++c) {
-          const int cell = ch * CPC + c;
-          // digits -> value: pairs of digits recombine exactly in int32 (|digit sum| <= 128 Kp <= 2^22), the rest in
-          // fp64 (every partial result is an integer below 2^53 times a power of two: no rounding anywhere)
+          // digits -> value: pairs of digits recombine exactly in int32 (|digit sum| <= 128 Kp <= 2^22), then block +
+          // tail in int64 (every term is an integer: no rounding before the one conversion to fp64)
           const int lo = (int)v[SLICES * c] + ((int)v[SLICES * c + 1] << 8);
-          double val = (double)lo * ci[c];
+          long long tot = (long long)lo + tl[c];
           if (SLICES == 4) {
             const int hi = (int)v[SLICES * c + 2] + ((int)v[SLICES * c + 3] << 8);
-            val = fma((double)hi, 65536.0 * ci[c], val);
+            tot += (long long)hi << 16;
           }
+          double x = (double)tot * ci[c];
           if (p.final) {
-            const int64_t j = j0 + cell;
-            if (srow && (full || j < p.N)) {
-              if (p.mode >= XF_SING) val += xform_value(p.mode, p.r0 ? p.r0[j] : 0.0, p.a0, p.a1) * nsv;
-              val *= inv;
-              if (p.colscale) val *= p.colscale[j];
-              vmin = fmin(vmin, val);
-            }
+            if (rankmode) x = fma(fb[c], nsv, x);
+            x *= inv;
+            if (p.colscale) x *= cs[c];
           }
-          if (srow && (full || j0 + cell < p.N)) __stcs(optr + (int64_t)cell * p.ld, val);
+          val[c] = x;
+        }
+        if (p.dbg & 8) {
+          double a = 0.0;
+#pragma unroll
+          for (int c = 0; c < CPC; ++c) a += val[c];
+          if (a == 1.2345e-300) optr[0] = a;
+        } else if (full && rows_full) {
+#pragma unroll
+          for (int c = 0; c < CPC; ++c) {
+            if (p.final) vmin = fmin(vmin, val[c]);
+            __stcs(optr + (int64_t)(ch * CPC + c) * p.ld, val[c]);
+          }
+        } else if (srow) {
+#pragma unroll
+          for (int c = 0; c < CPC; ++c)
+            if (full || jc + c < p.N) {
+              if (p.final) vmin = fmin(vmin, val[c]);
+              __stcs(optr + (int64_t)(ch * CPC + c) * p.ld, val[c]);
+            }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[as]));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&sm->acc_empty[as]));
+        if (has_tail) mbar_arrive(smem_u32(&sm->tail_empty[as]));
+      }
     }
     if (p.final && p.smin) {
       unsigned long long k = vmin == INFINITY ? ~0ull : key_of(vmin);
@@ -357,7 +424,9 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
                                                      double a1, int Kp, signed char* __restrict__ Bd,
                                                      double* __restrict__ colinv, int32_t* __restrict__ oi,
                                                      double* __restrict__ ox, int32_t* __restrict__ xe,
-                                                     int* __restrict__ flag) {
+                                                     int* __restrict__ flag, const int32_t* __restrict__ tmap,
+                                                     uint32_t* __restrict__ tcnt, int32_t Pt, int tileC,
+                                                     double* __restrict__ colfb) {
   extern __shared__ uint8_t prep_sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
   signed char* rows = reinterpret_cast<signed char*>(prep_sm) + (size_t)w * SLICES * Kp;  // [SLICES][Kp]
@@ -368,11 +437,13 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
     const int32_t c0 = xp[j], c1 = xp[j + 1];
     double fb = 0.0;
     if (mode >= XF_SING) fb = xform_value(mode, r0 ? r0[j] : 0.0, a0, a1);
-    // pass 1: largest |value| among the block entries of this column
+    if (colfb && lane == 0) colfb[j] = fb;
+    // pass 1: largest |value| among the block entries (and, with a tail pass, the tail entries) of this column
     double mx = 0.0;
     bool bad = false;
     for (int32_t e = c0 + lane; e < c1; e += 32) {
-      if (dmap[xi[e]] != 0xFFFFu) {
+      const int32_t r1 = xi[e];
+      if (dmap[r1] != 0xFFFFu || (tmap && tmap[r1] >= 0)) {
         double v = xform_value(mode, xx[e], a0, a1);
         if (mode >= XF_SING) v -= fb;
         const double a = fabs(v);
@@ -417,6 +488,10 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
         const int32_t q = o + __popc(mk & lt);
         oi[q] = r;
         ox[q] = x;
+        if (tmap) {  // entries per (cell tile, tail row): the gene-major regrouping of tail_kernels.cu
+          const int32_t g = tmap[r];
+          if (g >= 0) atomicAdd(tcnt + (size_t)(j / tileC) * Pt + g, 1u);
+        }
       }
       o += __popc(mk);
     }
@@ -502,7 +577,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-size_t tc_smem_bytes() { return (size_t)TC_BST * TC_BSTAGE + sizeof(TcSmem) + 1024; }
+size_t tc_smem_bytes() { return (size_t)TC_BST * TC_BSTAGE + 2 * (size_t)TC_TBUF + sizeof(TcSmem) + 1024; }
 
 }  // namespace
 
@@ -517,7 +592,7 @@ size_t tc_operand_bytes(int64_t N, int Kp, int slices) {
 cudaError_t launch_tc_prep_csc(const int32_t* xp, const int32_t* xi, const double* xx, const double* r0,
                                const uint16_t* dmap, int64_t N, int mode, double a0, double a1, int Kp, int slices,
                                signed char* Bd, double* colinv, int32_t* oi, double* ox, int32_t* xe, int* flag,
-                               cudaStream_t st) {
+                               const int32_t* tmap, uint32_t* tcnt, int32_t Pt, int tileC, double* colfb, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
   if (slices != 2 && slices != 4) return cudaErrorInvalidValue;
   const size_t per_warp = (size_t)slices * Kp;
@@ -530,9 +605,9 @@ cudaError_t launch_tc_prep_csc(const int32_t* xp, const int32_t* xi, const doubl
   int64_t grid = (N + warps - 1) / warps;
   if (grid > 148 * 8) grid = 148 * 8;
   if (slices == 2)
-    k_tc_prep_csc<2><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag);
+    k_tc_prep_csc<2><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag, tmap, tcnt, Pt, tileC, colfb);
   else
-    k_tc_prep_csc<4><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag);
+    k_tc_prep_csc<4><<<(unsigned)grid, warps * 32, smem, st>>>(xp, xi, xx, r0, dmap, N, mode, a0, a1, Kp, Bd, colinv, oi, ox, xe, flag, tmap, tcnt, Pt, tileC, colfb);
   return cudaGetLastError();
 }
 
@@ -552,6 +627,7 @@ cudaError_t launch_tc_score(const TcParams& p0, const signed char* Bd, int Kp, i
   EncodeTiledFn enc = encode_fn();
   if (!enc) return cudaErrorNotSupported;
   TcParams p = p0;
+  if (const char* e = getenv("PLAIDGPU_TC_DBG")) p.dbg = atoi(e);
   const int ct = TC_N / slices;
   p.ncell_tiles = (int)((p.N + ct - 1) / ct);
   p.kblocks = Kp / TC_KB;
@@ -564,6 +640,17 @@ cudaError_t launch_tc_score(const TcParams& p0, const signed char* Bd, int Kp, i
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorInvalidValue;
+  CUtensorMap mapT = map;  // unused without a tail
+  if (p.tail) {
+    if (slices != 4 || p.tail_ld < (int64_t)p.ncell_tiles * ct) return cudaErrorInvalidValue;
+    const cuuint64_t tdim[2] = {(cuuint64_t)p.tail_ld, (cuuint64_t)p.S};
+    const cuuint64_t tstr[1] = {(cuuint64_t)p.tail_ld * 8};
+    const cuuint32_t tbox[2] = {16, TC_M};
+    if (enc(&mapT, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<long long*>(p.tail), tdim, tstr, tbox, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
   const size_t smem = tc_smem_bytes();
   const void* fn = slices == 2 ? (const void*)k_tc_score<2> : (const void*)k_tc_score<4>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -587,8 +674,8 @@ cudaError_t launch_tc_score(const TcParams& p0, const signed char* Bd, int Kp, i
   }
   if (const char* e2 = getenv("PLAIDGPU_TC_CSPLIT")) best = std::max(1, std::min(atoi(e2), p.ncell_tiles));
   dim3 grid((unsigned)tiles_m, (unsigned)best);
-  if (slices == 2) k_tc_score<2><<<grid, TC_THREADS, smem, st>>>(map, p);
-  else k_tc_score<4><<<grid, TC_THREADS, smem, st>>>(map, p);
+  if (slices == 2) k_tc_score<2><<<grid, TC_THREADS, smem, st>>>(map, mapT, p);
+  else k_tc_score<4><<<grid, TC_THREADS, smem, st>>>(map, mapT, p);
   return cudaGetLastError();
 }
 
