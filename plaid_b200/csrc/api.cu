@@ -155,7 +155,7 @@ struct plaidgpu_ctx {
   // tail pass over every other row of a sparse X (tail_kernels.cu): Pt rows with a tail id, set-major member lists
   bool tail_on = false;
   int32_t Pt = 0;
-  DevBuf d_tmap, d_tptr, d_tidx, d_sorder, b_colfb, b_tcnt, b_trowptr, b_ttotal, b_tecell, b_teq, b_ttmp, b_tcounter;
+  DevBuf d_tmap, d_tptr, d_tidx, d_sorder, b_colfb, b_tcnt, b_trowptr, b_ttotal, b_tent, b_ttmp, b_tcounter;
 
   // current scoring call
   bool in_call = false, computed = false;
@@ -708,7 +708,7 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   DevBuf* bufs[] = {&c->d_ptr, &c->d_idx, &c->d_inv_mean, &c->d_inv_one, &c->d_ns, &c->d_custom_inv, &c->d_beta,
-                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->d_abits, &c->b_tcB, &c->b_colinv, &c->b_tcflag, &c->d_tmap, &c->d_tptr, &c->d_tidx, &c->d_sorder, &c->b_colfb, &c->b_tcnt, &c->b_trowptr, &c->b_ttotal, &c->b_tecell, &c->b_teq, &c->b_ttmp, &c->b_tcounter, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
+                    &c->d_dmap, &c->d_dptr, &c->d_didx, &c->d_colscale, &c->d_abits, &c->b_tcB, &c->b_colinv, &c->b_tcflag, &c->d_tmap, &c->d_tptr, &c->d_tidx, &c->d_sorder, &c->b_colfb, &c->b_tcnt, &c->b_trowptr, &c->b_ttotal, &c->b_tent, &c->b_ttmp, &c->b_tcounter, &c->b_xp, &c->b_xi, &c->b_xx, &c->b_rank, &c->b_r0, &c->b_colmax, &c->b_raw,
                     &c->b_med_all, &c->b_med_nz, &c->b_colmin, &c->b_scal, &c->b_i32, &c->b_dense, &c->b_rowa, &c->b_rowb, &c->b_fail, &c->b_list, &c->b_ci, &c->b_cx, &c->b_ce};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -1068,8 +1068,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       CK(c->b_tcnt.reserve((size_t)ctiles * c->Pt * sizeof(uint32_t) + 16));
       CK(c->b_trowptr.reserve((size_t)ctiles * (c->Pt + 1) * sizeof(uint32_t)));
       CK(c->b_ttotal.reserve((size_t)ctiles * sizeof(uint32_t)));
-      CK(c->b_tecell.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(uint16_t)));
-      CK(c->b_teq.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(int32_t)));
+      CK(c->b_tent.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(uint2)));
       CK(c->b_ttmp.reserve((size_t)c->S * (size_t)chunk * sizeof(long long)));
       CK(c->b_tcounter.reserve(sizeof(unsigned int)));
       CK(c->b_colfb.reserve((size_t)c->N * sizeof(double)));
@@ -1095,10 +1094,9 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
         CK(launch_tile_place(c->xp + j0, c->b_ce.as<int32_t>() + j0, c->b_ci.as<int32_t>(), c->b_cx.as<double>(),
                              p.r0 ? p.r0 + j0 : nullptr, c->d_tmap.as<int32_t>(), c->b_colinv.as<double>() + j0, nj, p.mode,
                              p.a0, p.a1, c->Pt, c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(),
-                             c->b_tcnt.as<uint32_t>(), c->b_tecell.as<uint16_t>(), c->b_teq.as<int32_t>(), tc_flag, c->stream));
+                             c->b_tcnt.as<uint32_t>(), c->b_tent.as<uint2>(), tc_flag, c->stream));
         CK(launch_tail(c->d_tptr.as<uint32_t>(), c->d_tidx.as<uint16_t>(), c->d_sorder.as<int32_t>(),
-                       c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(), c->b_tecell.as<uint16_t>(),
-                       c->b_teq.as<int32_t>(), c->S, c->Pt, tiles, c->b_ttmp.as<long long>(),
+                       c->b_trowptr.as<uint32_t>(), c->b_ttotal.as<uint32_t>(), c->b_tent.as<uint2>(), c->S, c->Pt, tiles, c->b_ttmp.as<long long>(),
                        c->b_tcounter.as<unsigned int>(), tc_flag, c->stream));
         c->launches += 3;
       }

@@ -155,10 +155,10 @@ int tail_tile_cells();
 cudaError_t launch_tile_scan(uint32_t* cnt, int32_t Pt, int tiles, uint32_t* rowptr, uint32_t* total, cudaStream_t st);
 cudaError_t launch_tile_place(const int32_t* xp, const int32_t* xe, const int32_t* oi, const double* ox, const double* r0,
                               const int32_t* tmap, const double* colinv, int64_t N, int mode, double a0, double a1,
-                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint16_t* ecell,
-                              int32_t* eq, const int* skip_if, cudaStream_t st);
+                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint2* ent,
+                              const int* skip_if, cudaStream_t st);
 cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_t* sorder, const uint32_t* rowptr,
-                        const uint32_t* total, const uint16_t* ecell, const int32_t* eq, int32_t S, int32_t Pt, int tiles,
+                        const uint32_t* total, const uint2* ent, int32_t S, int32_t Pt, int tiles,
                         long long* tmp, unsigned int* counter, const int* skip_if, cudaStream_t st);
 
 // stats_kernels.cu

@@ -4,8 +4,8 @@
 //
 // Formulation (replaces the lanes = genes scatter of score_kernels.cu on the fixed-point path):
 //   * the cells are cut into tiles of TAIL_C columns; per tile the tail entries of X are regrouped GENE-major
-//     (k_tile_scan / k_tile_place: counting sort by tail row -> `rowptr`, `ecell` (cell inside the tile, u16) and
-//     `eq` (the value in the column's fixed point, the same 2^e_j the tensor-core pass uses, int32));
+//     (k_tile_scan / k_tile_place: counting sort by tail row -> `rowptr` and 8-byte records `ent` = {value in the
+//     column's fixed point (the same 2^e_j the tensor-core pass uses, int32), cell inside the tile});
 //   * one warp owns one (tile, set) item at a time: it walks the set's tail members and adds each member's
 //     sparse row of the tile into TAIL_C accumulators in shared memory, LANES = the row's ENTRIES.  The cells
 //     of one row are distinct, and rows are handled one after the other, so there are no duplicate addresses
@@ -75,8 +75,7 @@ __global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ 
                                                     const double* __restrict__ colinv, int64_t N, int mode, double a0,
                                                     double a1, int32_t Pt, int C, const uint32_t* __restrict__ rowptr,
                                                     const uint32_t* __restrict__ total, uint32_t* __restrict__ cnt,
-                                                    uint16_t* __restrict__ ecell, int32_t* __restrict__ eq,
-                                                    const int* __restrict__ skip_if) {
+                                                    uint2* __restrict__ ent, const int* __restrict__ skip_if) {
   if (skip_if && *skip_if != 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -99,8 +98,7 @@ __global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ 
       double v = xform_value(mode, ox[e], a0, a1);
       if (mode >= XF_SING) v -= fb;
       const uint32_t pos = base + rp[g] + atomicAdd(cur + g, 1u);
-      ecell[pos] = (uint16_t)cell;
-      eq[pos] = (int32_t)__double2ll_rn(v * sc);
+      ent[pos] = make_uint2((uint32_t)(int32_t)__double2ll_rn(v * sc), cell);
     }
   }
 }
@@ -111,8 +109,7 @@ struct TailParams {
   const int32_t* sorder;   // [S] sets in decreasing order of their tail size
   const uint32_t* rowptr;  // [tiles][Pt + 1]
   const uint32_t* total;   // [tiles]
-  const uint16_t* ecell;
-  const int32_t* eq;
+  const uint2* ent;        // {fixed-point value, cell inside the tile}, gene-major per tile
   int32_t S, Pt, C, tiles;
   long long* tmp;          // [S][ld] int64 sums
   int64_t ld;              // = tiles * C
@@ -132,6 +129,7 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p)
     hi[c] = 0;
   }
   __syncwarp();
+  const uint32_t lo_sa = (uint32_t)__cvta_generic_to_shared(lo), hi_sa = (uint32_t)__cvta_generic_to_shared(hi);
   const unsigned nitems = (unsigned)p.tiles * (unsigned)p.S;
   for (;;) {
     unsigned item = 0;
@@ -145,8 +143,7 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p)
     for (int u = lane; u < t; u += 32) base += p.total[u];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(FULL, base, o);
-    const uint16_t* __restrict__ ec = p.ecell + base;
-    const int32_t* __restrict__ eqv = p.eq + base;
+    const uint2* __restrict__ ent = p.ent + base;
     const uint32_t m0 = p.tptr[s], m1 = p.tptr[s + 1];
     for (uint32_t mb = m0; mb < m1; mb += 32) {
       // lane i looks up the row of member mb + i in this tile
@@ -157,59 +154,55 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p)
         rn = rp[g + 1] - r0;
       }
       const int cnt = (int)min(32u, m1 - mb);
-      // software pipeline over the (member, 32-entry segment) sequence: four segments are in flight (their entries
-      // come from L2, ~300 clocks away), added in fetch order
-      int fk = 0;          // fetch cursor: member
-      uint32_t foff = 0;   //               offset inside its row
-      auto fetch = [&](uint32_t& cc, int32_t& qq) -> bool {
-        uint32_t nk = 0;
-        while (fk < cnt) {
-          nk = __shfl_sync(FULL, rn, fk);
-          if (foff < nk) break;
-          ++fk;
-          foff = 0;
-        }
-        cc = 0xFFFFu;
-        qq = 0;
-        if (fk >= cnt) return false;
-        const uint32_t pk = __shfl_sync(FULL, r0, fk);
-        const uint32_t i = foff + (uint32_t)lane;
-        if (i < nk) {
-          cc = ec[pk + i];
-          qq = eqv[pk + i];
-        }
-        foff += 32;
-        return true;
-      };
-      auto add = [&](uint32_t c, int32_t q) {
-        if (c != 0xFFFFu) {
-          const uint32_t uq = (uint32_t)q;
-          const uint32_t nv = lo[c] + uq;
-          lo[c] = nv;
-          const int d = (nv < uq ? 1 : 0) - (q < 0 ? 1 : 0);  // carry out of / borrow from the low word
-          if (d != 0) hi[c] = (short)(hi[c] + d);
+      // member k's row: segments of 32 entries, lanes = entries.  The first segments of the next four members are
+      // in flight while a member is added (entries come from L2, ~350 clocks away; most rows are one segment)
+      auto add = [&](const uint2 rec) {
+        if (rec.y != 0xFFFFu) {
+          const uint32_t a = lo_sa + rec.y * 4u;
+          uint32_t old;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(a) : "memory");
+          const uint32_t nv = old + rec.x;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(nv) : "memory");
+          // carry out of the low word vs. sign extension of the addend: equal -> the high word keeps its value
+          if ((nv < rec.x) != ((int32_t)rec.x < 0)) {
+            const uint32_t ah = hi_sa + rec.y * 2u;
+            short hv;
+            asm volatile("ld.shared.s16 %0, [%1];" : "=h"(hv) : "r"(ah) : "memory");
+            hv = (short)(hv + ((nv < rec.x) ? 1 : -1));
+            asm volatile("st.shared.s16 [%0], %1;" ::"r"(ah), "h"(hv) : "memory");
+          }
         }
         __syncwarp();
       };
-      uint32_t c0, c1, c2, c3;
-      int32_t q0, q1, q2, q3;
-      bool ok0 = fetch(c0, q0);
-      bool ok1 = ok0 && fetch(c1, q1);
-      bool ok2 = ok1 && fetch(c2, q2);
-      bool ok3 = ok2 && fetch(c3, q3);
-      for (;;) {
-        if (!ok0) break;
-        add(c0, q0);
-        ok0 = ok3 && fetch(c0, q0);
-        if (!ok1) break;
-        add(c1, q1);
-        ok1 = ok0 && fetch(c1, q1);
-        if (!ok2) break;
-        add(c2, q2);
-        ok2 = ok1 && fetch(c2, q2);
-        if (!ok3) break;
-        add(c3, q3);
-        ok3 = ok2 && fetch(c3, q3);
+      auto prefetch = [&](int kk, uint2& rec, uint32_t& nk, uint32_t& pk) {
+        nk = kk < cnt ? __shfl_sync(FULL, rn, kk & 31) : 0u;
+        pk = __shfl_sync(FULL, r0, kk & 31);
+        rec = make_uint2(0u, 0xFFFFu);
+        if ((uint32_t)lane < nk) rec = __ldg(ent + pk + lane);
+      };
+      auto member = [&](const uint2 rec, uint32_t nk, uint32_t pk) {
+        add(rec);
+        for (uint32_t off = 32; off < nk; off += 32) {  // long rows: further segments
+          uint2 r2 = make_uint2(0u, 0xFFFFu);
+          if (off + lane < nk) r2 = __ldg(ent + pk + off + lane);
+          add(r2);
+        }
+      };
+      uint2 e0, e1, e2, e3;
+      uint32_t n0, n1, n2, n3, p0, p1, p2, p3;
+      prefetch(0, e0, n0, p0);
+      prefetch(1, e1, n1, p1);
+      prefetch(2, e2, n2, p2);
+      prefetch(3, e3, n3, p3);
+      for (int k = 0; k < cnt; k += 4) {
+        member(e0, n0, p0);
+        prefetch(k + 4, e0, n0, p0);
+        member(e1, n1, p1);
+        prefetch(k + 5, e1, n1, p1);
+        member(e2, n2, p2);
+        prefetch(k + 6, e2, n2, p2);
+        member(e3, n3, p3);
+        prefetch(k + 7, e3, n3, p3);
       }
     }
     // flush: int64 sums of set s over the tile's cells, coalesced; re-zero
@@ -238,18 +231,18 @@ cudaError_t launch_tile_scan(uint32_t* cnt, int32_t Pt, int tiles, uint32_t* row
 
 cudaError_t launch_tile_place(const int32_t* xp, const int32_t* xe, const int32_t* oi, const double* ox, const double* r0,
                               const int32_t* tmap, const double* colinv, int64_t N, int mode, double a0, double a1,
-                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint16_t* ecell,
-                              int32_t* eq, const int* skip_if, cudaStream_t st) {
+                              int32_t Pt, const uint32_t* rowptr, const uint32_t* total, uint32_t* cnt, uint2* ent,
+                              const int* skip_if, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
   int64_t grid = (N + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
   k_tile_place<<<(unsigned)grid, 256, 0, st>>>(xp, xe, oi, ox, r0, tmap, colinv, N, mode, a0, a1, Pt, tail_tile_cells(),
-                                               rowptr, total, cnt, ecell, eq, skip_if);
+                                               rowptr, total, cnt, ent, skip_if);
   return cudaGetLastError();
 }
 
 cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_t* sorder, const uint32_t* rowptr,
-                        const uint32_t* total, const uint16_t* ecell, const int32_t* eq, int32_t S, int32_t Pt, int tiles,
+                        const uint32_t* total, const uint2* ent, int32_t S, int32_t Pt, int tiles,
                         long long* tmp, unsigned int* counter, const int* skip_if, cudaStream_t st) {
   if (tiles <= 0 || S <= 0) return cudaSuccess;
   TailParams p{};
@@ -258,8 +251,7 @@ cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_
   p.sorder = sorder;
   p.rowptr = rowptr;
   p.total = total;
-  p.ecell = ecell;
-  p.eq = eq;
+  p.ent = ent;
   p.S = S;
   p.Pt = Pt;
   p.C = tail_tile_cells();

@@ -146,6 +146,54 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
+// Epilogue of one 32-column chunk (8 cells x 4 digit columns) of a tile whose cells and rows are all valid, final
+// scores (the common case, instruction-minimal: one warp per scheduler cannot hide its own latencies, and the fp64
+// pipe is narrow).  Per cell: digits + tail -> int64 (exact), ONE int -> fp64 conversion, the column's power-of-two
+// scale applied by an integer add on the exponent field, one DMUL by 1 / (n_s + 1e-8); the sign class of the scores
+// (any negative / any zero, all normalize_medians needs up front) is tracked with integer ops.
+template <bool RANK, bool CS>
+__device__ __forceinline__ void tc_epi_fast(const uint32_t (&v)[32], uint32_t trow, uint32_t tsw, bool has_tail, int ch,
+                                            const TcParams& p, int64_t jc, double inv, double nsv, double* __restrict__ o,
+                                            uint32_t& negbits, bool& anyzero) {
+  int ed[8];
+  double fb[8], cs[8];
+  long long tl[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    ed[c] = __ldg(reinterpret_cast<const int*>(p.colinv + jc + c) + 1) - 0x3FF00000;  // (exponent of 2^-e_j) << 20
+    if (RANK) fb[c] = __ldg(p.colfb + jc + c);
+    if (CS) cs[c] = __ldg(p.colscale + jc + c);
+    tl[c] = 0;
+  }
+  if (has_tail) {
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const int cell = ch * 8 + c;  // even: cells c, c + 1 share one 16-byte chunk
+      const uint32_t a = trow + (uint32_t)(cell >> 4) * TC_TBOX + ((((uint32_t)(cell & 15) >> 1) ^ tsw) << 4);
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(tl[c]), "=l"(tl[c + 1]) : "r"(a));
+    }
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int lo = (int)v[4 * c] + ((int)v[4 * c + 1] << 8);
+    const int hi = (int)v[4 * c + 2] + ((int)v[4 * c + 3] << 8);
+    const long long tot = (long long)hi * 65536ll + tl[c] + (long long)lo;
+    double x = (double)tot;
+    int xh = __double2hiint(x);
+    xh = tot != 0 ? xh + ed[c] : xh;  // x * 2^-e_j (prep keeps e_j far from the exponent limits)
+    x = __hiloint2double(xh, __double2loint(x));
+    if (RANK) x = fma(fb[c], nsv, x);
+    x *= inv;
+    if (CS) x *= cs[c];
+    const uint32_t h = (uint32_t)__double2hiint(x);
+    negbits |= h;
+    anyzero = anyzero || (((h << 1) | (uint32_t)__double2loint(x)) == 0u);
+    __stcs(o, x);
+    o += p.ld;
+  }
+}
+
 template <int SLICES>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constant__ CUtensorMap tmapB,
                                                             const __grid_constant__ CUtensorMap tmapT, const TcParams p) {
@@ -297,6 +345,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     }
     const bool rankmode = p.final && p.mode >= XF_SING;
     double vmin = INFINITY;
+    uint32_t negbits = 0;   // fast path: OR of the high words of the scores (sign bit = some score is negative)
+    bool anyzero = false;   //            some score is exactly zero
+    const bool fastable = SLICES == 4 && p.final && rows_full && (!rankmode || p.colfb != nullptr) && !(p.dbg & 32);
     constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
     const uint32_t tsw = (uint32_t)(lane & 7);
     for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
@@ -313,6 +364,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       for (int ch = wh; ch < ((p.dbg & 16) ? 0 : TC_N / 32); ch += 2) {
         uint32_t v[32];
         tc_ld32(tmem + lane_base + as * TC_N + ch * 32, v);
+        if (SLICES == 4 && fastable && full) {
+          double* o = optr + (int64_t)(ch * 8) * p.ld;
+          const int64_t jc8 = j0 + ch * 8;
+          if (rankmode) {
+            if (p.colscale) tc_epi_fast<true, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+            else tc_epi_fast<true, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+          } else {
+            if (p.colscale) tc_epi_fast<false, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+            else tc_epi_fast<false, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+          }
+          continue;
+        }
         double ci[CPC], fb[CPC], cs[CPC];
         long long tl[CPC];
         const int64_t jc = j0 + ch * CPC;
@@ -380,6 +443,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       }
     }
     if (p.final && p.smin) {
+      // the fast path tracked only the sign class of its scores; a representative stands in for the minimum (the
+      // host looks at the sign of the result and nothing else, api.cu)
+      if (negbits >> 31) vmin = fmin(vmin, -1.0);
+      else if (anyzero) vmin = fmin(vmin, 0.0);
+      else if (negbits) vmin = fmin(vmin, 1.0);
       unsigned long long k = vmin == INFINITY ? ~0ull : key_of(vmin);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -457,7 +525,11 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
       if (lane == 0) atomicExch(flag, 1);
       mx = 0.0;
     }
-    const int ex = scale_exp(mx, SLICES);
+    int ex = scale_exp(mx, SLICES);
+    if (ex < -900 || ex > 900) {  // the epilogue scales by an integer add on the exponent field: keep clear of its limits
+      if (lane == 0) atomicExch(flag, 1);
+      ex = 0;
+    }
     const double sc = ldexp(1.0, ex);
     if (lane == 0) colinv[j] = ldexp(1.0, -ex);
     __syncwarp();
@@ -534,7 +606,11 @@ __global__ void __launch_bounds__(256) k_tc_prep_dense(const double* __restrict_
       if (tid == 0) atomicExch(flag, 1);
       mx = 0.0;
     }
-    const int ex = scale_exp(mx, SLICES);
+    int ex = scale_exp(mx, SLICES);
+    if (ex < -900 || ex > 900) {  // as in k_tc_prep_csc
+      if (tid == 0) atomicExch(flag, 1);
+      ex = 0;
+    }
     const double sc = ldexp(1.0, ex);
     if (tid == 0) colinv[j] = ldexp(1.0, -ex);
     signed char* __restrict__ rows = Bd + (size_t)j * SLICES * Kp;
