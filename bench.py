@@ -120,6 +120,48 @@ def make_inputs(dev, rank, n_cells):
     return G, p, i, x
 
 
+WORKLOADS = {
+    # name: (scorer constant name, opts, human description, BASELINE.json config)
+    "plaid": ("PLAID", dict(stats_mean=1, normalize=1), "plaid(): stats=mean, normalize=TRUE", "configs[3] (C4) as its per-GPU shard"),
+    "ssgsea": ("SSGSEA", dict(alpha=0.0), "replaid.ssgsea(alpha=0): sparse_colranks + rank-weighted product + median normalisation",
+               "configs[2] (C3) / north star's second target, on the C4 shard"),
+    "ucell": ("UCELL", dict(rmax=1500.0), "replaid.ucell(rmax=1500): dense-semantics column ranks + product + normalisation",
+              "configs[4] (C5) as its per-GPU shard"),
+    "plaid_dense": ("PLAID", dict(stats_mean=1, normalize=1), "plaid() on a dense bulk matrix: stats=mean, normalize=TRUE", "configs[1] (C2)"),
+}
+DENSE_N = 1000
+
+
+def host_mem_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 8 << 30
+
+
+def pcie_floor(torch, dev, nbytes, world, dist):
+    """raw D2H rate of this box with all ranks copying at once (pinned destination, 256 MB pieces): the floor of the
+    host-output e2e leg is d2h_bytes / this rate"""
+    n = min(nbytes, 1 << 30)
+    src = torch.empty(n // 8, dtype=torch.float64, device=dev)
+    dst = torch.empty(n // 8, dtype=torch.float64).pin_memory()
+    dst.copy_(src)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return n * reps / float(t[0]) / 1e9  # GB/s per GPU with `world` GPUs active
+
+
 # ---------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch
@@ -147,19 +189,36 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    Nc = a.cells_per_gpu
-    G, xp, xi, xx = make_inputs(dev, rank, Nc)
-    nnz = int(xx.numel())
+    wl = a.workload
+    scorer_name, okw, wl_desc, wl_cfg = WORKLOADS[wl]
+    dense = wl == "plaid_dense"
+    Nc = DENSE_N if dense else a.cells_per_gpu
     names = synth.gene_names(P_GENES)
     rowmap = pb.make_rowmap(names, names)
     ctx = pb.Context(local)
-    ctx.set_genesets(G)
     lib = ctx.lib
-    out = torch.empty(S_SETS * Nc, dtype=torch.float64, device=dev)
     keep: list = []
     from plaid_b200.api import _matrix_struct, _opts
-    M = _matrix_struct(pb.DeviceCSC(xp, xi, xx, (P_GENES, Nc)), keep)
-    opts = _opts(lib, scorer=L.PLAID, stats_mean=1, normalize=1, out_location=L.DEVICE)
+    if dense:
+        # C2: every rank scores its own replica of the 20,000 x 1,000 bulk matrix ("replicas only")
+        import scipy.sparse as sp
+        Gp, Gi = synth.genesets_torch(P_GENES, S_SETS, seed=synth.SEED0 + 3, device=dev)
+        G = sp.csc_matrix((np.ones(Gi.size), Gi, Gp), shape=(P_GENES, S_SETS))
+        Xh = synth.dense_x_numpy(P_GENES, Nc, seed=synth.SEED0 + 1 + rank)
+        xd = torch.from_numpy(np.ascontiguousarray(Xh.T)).to(dev)  # N x P row-major == the bytes of P x N column-major
+        M = L.Matrix()
+        M.kind, M.location, M.P, M.N = L.DENSE, L.DEVICE, P_GENES, Nc
+        M.p, M.i, M.x = None, None, xd.data_ptr()
+        nnz = P_GENES * Nc
+        xp = xi = xx = None
+    else:
+        G, xp, xi, xx = make_inputs(dev, rank, Nc)
+        nnz = int(xx.numel())
+        M = _matrix_struct(pb.DeviceCSC(xp, xi, xx, (P_GENES, Nc)), keep)
+    ctx.set_genesets(G)
+    out = torch.empty(S_SETS * Nc, dtype=torch.float64, device=dev)
+    scorer = getattr(L, scorer_name)
+    opts = _opts(lib, scorer=scorer, out_location=L.DEVICE, **okw)
 
     def step():
         return sharded.score_shard(ctx, comm, M, rowmap, opts, out.data_ptr(), Nc)
@@ -172,97 +231,171 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     k_ms = np.zeros(4)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step()
-        k_ms += [ctx.kernel_ms(k) for k in range(4)]
-    barrier()
-    dt = time.perf_counter() - t0
+    flush = torch.empty(1 << 27, dtype=torch.float32, device=dev) if dense else None  # 512 MB > L2 (C2 fits L2 otherwise)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dt = 0.0
+    if dense:
+        # the C2 working set (411 MB) is L2-sized: flush L2 between timed steps, time each step on its own
+        for _ in range(a.steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            step()
+            torch.cuda.synchronize()
+            dt += time.perf_counter() - t0
+            k_ms += [ctx.kernel_ms(k) for k in range(4)]
+        barrier()
+    else:
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step()
+            k_ms += [ctx.kernel_ms(k) for k in range(4)]
+        barrier()
+        dt = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count()
-    tt = torch.tensor([dt, float(launches), k_ms[0], float(nnz)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dt, float(launches), k_ms[0], float(nnz), k_ms[3]], dtype=torch.float64, device=dev)
     if dist is not None:
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dt, launches, score_ms_sum, nnz_tot = float(mx[0]), int(sm[1]), float(mx[2]), float(sm[3])
+        dt, launches, score_ms_sum, nnz_tot, rank_ms_sum = float(mx[0]), int(sm[1]), float(mx[2]), float(sm[3]), float(mx[4])
     else:
-        score_ms_sum, nnz_tot = float(k_ms[0]), float(nnz)
+        score_ms_sum, nnz_tot, rank_ms_sum = float(k_ms[0]), float(nnz), float(k_ms[3])
     value = S_SETS * float(Nc) * world * a.steps / dt
 
-    # ---- roofline of the dominant kernel (k_score): SURVEY §8(d) algorithmic bytes per launch -------
+    # ---- roofline of the dominant kernel group (the score product): SURVEY §8(d) algorithmic bytes per launch ----
     nnzG = int(G.nnz)
-    alg_bytes = nnz * 12 + (Nc + 1) * 4 + nnzG * 4 + (S_SETS + 1) * 4 + S_SETS * Nc * 8
+    if dense:
+        alg_bytes = P_GENES * Nc * 8 + nnzG * 4 + S_SETS * Nc * 8
+        alg_formula = "P*N*8 + nnzG*4 + S*N*8 (dense X)"
+    else:
+        alg_bytes = nnz * 12 + (Nc + 1) * 4 + nnzG * 4 + (S_SETS + 1) * 4 + S_SETS * Nc * 8
+        alg_formula = "nnzX*12 + (N+1)*4 + nnzG*4 + (S+1)*4 + S*N*8"
+        if wl in ("ssgsea", "ucell"):
+            alg_bytes += nnz * 8  # fused rank scorers: the ranks are read once more (B_plaid + nnzX*8)
+            alg_formula += " + nnzX*8 (ranks)"
     score_ms = score_ms_sum / a.steps
     peak, peak_src = peaks()
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9
     traffic = None
     tnote = None
+    pipes = None
     try:
         with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as fh:
             tj = json.load(fh)
-        traffic = float(tj["dram_bytes_per_cell"]) * Nc
+        if not dense:
+            traffic = float(tj["dram_bytes_per_cell"]) * Nc
         tnote = tj.get("note")
+        pipes = tj.get("pipes")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "score product = k_gather + k_scatter launch pair (CUDA events around both)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "score product = k_tc_prep + k_tile_scan/place + k_tail + k_tc_score (CUDA events around the group, library stream)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": tnote, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": round(score_ms, 3),
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_formula": alg_formula, "launch_ms": round(score_ms, 3),
                 "kernel_share_of_step": round(score_ms / (dt / a.steps * 1e3), 3),
                 "ms_per_step_by_kernel": {"score": round(k_ms[0] / a.steps, 3), "colstats": round(k_ms[1] / a.steps, 3),
-                                          "fixup": round(k_ms[2] / a.steps, 3)},
+                                          "fixup": round(k_ms[2] / a.steps, 3), "rank": round(k_ms[3] / a.steps, 3)},
+                "on_chip_pipes": pipes,
                 "plan": ctx.plan_info()}
 
-    # ---- e2e: public API, HOST pinned buffers, H2D + D2H inside the timed region ---------------------
+    # ---- e2e: public API / C ABI, HOST buffers, H2D + D2H inside the timed region ------------------------------
     e2e = None
     if a.e2e_cells != 0:
-        Ne = min(a.e2e_cells if a.e2e_cells > 0 else 32768, Nc)
-        hp = torch.empty(Ne + 1, dtype=torch.int32).pin_memory()
-        hp.copy_(xp[:Ne + 1])
-        ne = int(hp[Ne])
-        hi = torch.empty(ne, dtype=torch.int32).pin_memory(); hi.copy_(xi[:ne])
-        hx = torch.empty(ne, dtype=torch.float64).pin_memory(); hx.copy_(xx[:ne])
+        Ne = Nc if a.e2e_cells < 0 else min(a.e2e_cells, Nc)
+        # the full shard when the host can hold two S x N results (pinned + pageable legs run one after the other)
+        avail = host_mem_available() // max(1, world)
+        per_cell = S_SETS * 8
+        if Ne * per_cell > 0.4 * avail:
+            Ne = max(1024, int(0.4 * avail / per_cell) // 1024 * 1024)
+        Ne = min(Ne, Nc)
+        if dense:
+            hx = torch.from_numpy(np.ascontiguousarray(Xh.T)).pin_memory()
+            Mh = L.Matrix()
+            Mh.kind, Mh.location, Mh.P, Mh.N = L.DENSE, L.HOST, P_GENES, Ne
+            Mh.p, Mh.i, Mh.x = None, None, hx.data_ptr()
+            h2d = P_GENES * Ne * 8
+        else:
+            hp = torch.empty(Ne + 1, dtype=torch.int32).pin_memory()
+            hp.copy_(xp[:Ne + 1])
+            ne = int(hp[Ne])
+            hi = torch.empty(ne, dtype=torch.int32).pin_memory(); hi.copy_(xi[:ne])
+            hx = torch.empty(ne, dtype=torch.float64).pin_memory(); hx.copy_(xx[:ne])
+            Mh = L.Matrix()
+            Mh.kind, Mh.location, Mh.P, Mh.N = L.CSC, L.HOST, P_GENES, Ne
+            Mh.p, Mh.i, Mh.x = hp.data_ptr(), hi.data_ptr(), hx.data_ptr()
+            h2d = (Ne + 1) * 4 + ne * 12
+        oh = _opts(lib, scorer=scorer, out_location=L.HOST, **okw)
+        d2h = S_SETS * Ne * 8
+        floor_gbs = pcie_floor(torch, dev, d2h, world, dist)
+
+        def leg(out_ptr, probe):
+            def estep():
+                return sharded.score_shard(ctx, comm, Mh, rowmap, oh, out_ptr, Ne)
+            estep(); estep()  # the second call sizes its early-shipped part from the first one's measured rates
+            barrier()
+            ke = max(1, min(a.steps, 3 if Ne * per_cell > (8 << 30) else 5))
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                estep()
+                _ = probe()  # the result is read on the host
+            barrier()
+            edt = time.perf_counter() - t0
+            et = torch.tensor([edt], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            return float(et[0]) / ke, ke
+
         hout = torch.empty(S_SETS * Ne, dtype=torch.float64).pin_memory()
-        Mh = L.Matrix()
-        Mh.kind, Mh.location, Mh.P, Mh.N = L.CSC, L.HOST, P_GENES, Ne
-        Mh.p, Mh.i, Mh.x = hp.data_ptr(), hi.data_ptr(), hx.data_ptr()
-        oh = _opts(lib, scorer=L.PLAID, stats_mean=1, normalize=1, out_location=L.HOST)
-
-        def estep():
-            return sharded.score_shard(ctx, comm, Mh, rowmap, oh, hout.data_ptr(), Ne)
-
-        estep()
-        barrier()
-        ke = max(1, min(a.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            estep()
-            _ = float(hout[0])  # the result is read on the host
-        barrier()
-        edt = time.perf_counter() - t0
-        et = torch.tensor([edt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e = {"value": S_SETS * float(Ne) * world * ke / float(et[0]), "unit": UNIT,
-               "h2d_bytes_per_step": int((Ne + 1) * 4 + ne * 12) * world, "d2h_bytes_per_step": int(S_SETS * Ne * 8) * world,
-               "cells_per_gpu": Ne, "steps": ke, "ms_per_step": round(float(et[0]) / ke * 1e3, 2),
-               "note": "host buffers pinned; same plaid() path incl. normalisation; sample of the shard's first cells"}
-        del hout, hx, hi
+        sec, ke = leg(hout.data_ptr(), lambda: float(hout[0]) + float(hout[-1]))
+        del hout
+        e2e = {"value": S_SETS * float(Ne) * world / sec, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "cells_per_gpu": Ne, "steps": ke, "ms_per_step": round(sec * 1e3, 2),
+               "pcie_d2h_gbs_per_gpu": round(floor_gbs, 1), "pcie_floor_ms": round(d2h / floor_gbs / 1e6, 2),
+               "frac_of_pcie_floor": round((d2h / floor_gbs / 1e9) / sec, 3),
+               "note": "host buffers pinned; the same call incl. normalisation; H2D of X and D2H of the S x N result inside the timed "
+                       "region (chunks of raw scores leave while later chunks are scored); pcie_floor_ms = d2h bytes / the box's measured "
+                       "concurrent D2H rate"}
+        # what an R caller gets: pageable (malloc) buffers on both sides, the library's pinned ring + copy threads
+        try:
+            pout = np.empty(S_SETS * Ne, dtype=np.float64)
+            if dense:
+                px = np.array(hx.numpy(), copy=True)
+                Mh.x = px.ctypes.data
+            else:
+                pp, pi, px = (np.array(t.numpy(), copy=True) for t in (hp, hi, hx))
+                Mh.p, Mh.i, Mh.x = pp.ctypes.data, pi.ctypes.data, px.ctypes.data
+            sec2, ke2 = leg(pout.ctypes.data, lambda: float(pout[0]) + float(pout[-1]))
+            e2e["pageable"] = {"value": S_SETS * float(Ne) * world / sec2, "unit": UNIT, "ms_per_step": round(sec2 * 1e3, 2), "steps": ke2,
+                               "note": "plain malloc buffers for X and the result (what the R shim passes): pinned ring + copy threads inside the library"}
+            del pout
+        except MemoryError:
+            e2e["pageable"] = None
+        del hx
 
     # ---- CPU baseline: oracle port, 1 core, bounded sample (rank 0, N = 1 only) -----------------------
     cpu = None
     if rank == 0 and world == 1 and a.cpu_cells > 0:
-        cpu = cpu_baseline(G, xp, xi, xx, min(a.cpu_cells, Nc), names)
+        if dense:
+            cpu = cpu_baseline_dense(G, Xh, names, wl)
+        else:
+            cpu = cpu_baseline(G, xp, xi, xx, min(a.cpu_cells if wl == "plaid" else max(500, a.cpu_cells // 3), Nc), names, wl)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        shape = (f"dense bulk matrix {P_GENES} genes x {Nc} samples per GPU (replicas)" if dense else
+                 f"sparse dgCMatrix {P_GENES} genes x {Nc} cells/GPU (~7% nnz, pbmc3k-shaped)")
+        line = {"metric": METRIC if wl.startswith("plaid") else METRIC.replace("plaid()", f"replaid.{wl}()"),
+                "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C4-shard plaid(): sparse dgCMatrix {P_GENES} genes x {Nc} cells/GPU (~7% nnz, "
-                                       f"pbmc3k-shaped), {S_SETS} MSigDB-scale gene sets, stats=mean, normalize=TRUE; "
-                                       f"C4 (1M cells) = 8 such shards",
+                "config": {"workload": f"{wl}: {wl_desc}; {shape}, {S_SETS} MSigDB-scale gene sets; BASELINE.json {wl_cfg}",
                            "genes": P_GENES, "cells_per_gpu": Nc, "cells_total": Nc * world, "gene_sets": S_SETS,
                            "nnz_x_per_gpu": nnz, "nnz_g": nnzG, "sharding": f"columns x{world}, no data-path collective",
-                           "l2": "inputs_exceed_l2 (X 2.1 GB + out 30 GB per GPU vs 126 MB L2; no flush needed)",
+                           "l2": ("l2_flushed between timed steps (512 MB write): the 411 MB working set is L2-sized" if dense else
+                                  "inputs_exceed_l2 (X 2.1 GB + out 30 GB per GPU vs 126 MB L2; no flush needed)"),
+                           "precision": "30-bit per-column fixed point on the tensor cores + integer tail sums (exact integer accumulation), "
+                                        "fp64 epilogue: <= 2e-9 relative to the oracle at this shape (tests/test_gpu_parity.py); north star allows 1e-6",
                            "timing": "K steps bracketed by barrier + cuda synchronize, max over ranks"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         _emit(line)
@@ -271,8 +404,34 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def cpu_baseline(G, xp, xi, xx, n, names):
-    """Oracle plaid() (scipy Gustavson product + densify + median normalisation) on ONE core."""
+def _oracle_fn(wl):
+    from oracle import plaid_oracle as O
+    return {"plaid": O.plaid, "plaid_dense": O.plaid, "ssgsea": O.replaid_ssgsea, "ucell": O.replaid_ucell}[wl]
+
+
+def cpu_baseline_dense(G, Xh, names, wl):
+    """Oracle plaid() on the dense C2 matrix, one core, a bounded column sample."""
+    from oracle import plaid_oracle as O
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    n = 64
+    Xn, Gn = O.Named(np.asfortranarray(Xh[:, :n]), names, None), O.Named(G, names, None)
+    t0 = time.perf_counter()
+    if threadpool_limits:
+        with threadpool_limits(limits=1):
+            _oracle_fn(wl)(Xn, Gn)
+    else:
+        _oracle_fn(wl)(Xn, Gn)
+    dt = time.perf_counter() - t0
+    return {"value": S_SETS * float(n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {n} samples x all {S_SETS} sets, oracle/plaid_oracle (numpy/scipy restatement of R/plaid.R; R itself is not "
+                      f"installable here), {dt:.1f} s", "seconds": round(dt, 2)}
+
+
+def cpu_baseline(G, xp, xi, xx, n, names, wl="plaid"):
+    """Oracle scorer (scipy Gustavson product + densify + median normalisation; ranks via rankdata) on ONE core."""
     import scipy.sparse as sp
     from oracle import plaid_oracle as O
     try:
@@ -284,14 +443,15 @@ def cpu_baseline(G, xp, xi, xx, n, names):
     X = sp.csc_matrix((xx[:ne].cpu().numpy(), xi[:ne].cpu().numpy(), hp), shape=(P_GENES, n))
     Xn, Gn = O.Named(X, names, None), O.Named(G, names, None)
     t0 = time.perf_counter()
+    fn = _oracle_fn(wl)
     if threadpool_limits:
         with threadpool_limits(limits=1):
-            r = O.plaid(Xn, Gn)
+            r = fn(Xn, Gn)
     else:
-        r = O.plaid(Xn, Gn)
+        r = fn(Xn, Gn)
     dt = time.perf_counter() - t0
     res = {"value": S_SETS * float(n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": f"first {n} cells of the shard x all {S_SETS} sets, oracle/plaid_oracle.plaid (numpy/scipy restatement "
+           "sample": f"first {n} cells of the shard x all {S_SETS} sets, oracle/plaid_oracle.{fn.__name__} (numpy/scipy restatement "
                      f"of R/plaid.R; R itself is not installable here), {dt:.1f} s",
            "seconds": round(dt, 2)}
     del r
@@ -306,6 +466,19 @@ def _w_init(Gd, Gi, Gp, names):
     import scipy.sparse as sp
     _W["G"] = sp.csc_matrix((Gd, Gi, Gp), shape=(P_GENES, S_SETS))
     _W["names"] = names
+
+
+def _w_whole(args):
+    """one column block through the whole oracle scorer (rank scorers, dense plaid)"""
+    import scipy.sparse as sp
+    from oracle import plaid_oracle as O
+    wl, d, i, p, n = args
+    if wl == "plaid_dense":
+        X = np.asfortranarray(d.reshape((n, P_GENES)).T)
+    else:
+        X = sp.csc_matrix((d, i, p), shape=(P_GENES, n))
+    r = _oracle_fn(wl)(O.Named(X, _W["names"], None), O.Named(_W["G"], _W["names"], None)).mat
+    return float(r[0, 0])
 
 
 def _w_phase1(args):
@@ -343,20 +516,32 @@ def run_reference(a):
     from plaid_b200 import synth
     cores = os.cpu_count() or 1
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"  # data generation only
-    per_core = 400
+    wl = a.workload
+    per_core = {"plaid": 400, "ssgsea": 150, "ucell": 150, "plaid_dense": 16}[wl]
     n = per_core * cores
-    G, xp, xi, xx = make_inputs(dev, 0, n)
     names = synth.gene_names(P_GENES)
-    hp = xp.cpu().numpy(); hi = xi.cpu().numpy(); hx = xx.cpu().numpy()
     blocks = []
-    for w in range(cores):
-        lo, hi_ = w * per_core, (w + 1) * per_core
-        e0, e1 = int(hp[lo]), int(hp[hi_])
-        blocks.append((hx[e0:e1], hi[e0:e1], (hp[lo:hi_ + 1] - e0).astype(np.int32), per_core))
+    if wl == "plaid_dense":
+        import scipy.sparse as sp
+        Gp, Gi = synth.genesets_torch(P_GENES, S_SETS, seed=synth.SEED0 + 3, device=dev)
+        G = sp.csc_matrix((np.ones(Gi.size), Gi, Gp), shape=(P_GENES, S_SETS))
+        Xh = synth.dense_x_numpy(P_GENES, n, seed=synth.SEED0 + 1)
+        for w in range(cores):
+            blocks.append((np.ascontiguousarray(Xh[:, w * per_core:(w + 1) * per_core].T).ravel(), None, None, per_core))
+    else:
+        G, xp, xi, xx = make_inputs(dev, 0, n)
+        hp = xp.cpu().numpy(); hi = xi.cpu().numpy(); hx = xx.cpu().numpy()
+        for w in range(cores):
+            lo, hi_ = w * per_core, (w + 1) * per_core
+            e0, e1 = int(hp[lo]), int(hp[hi_])
+            blocks.append((hx[e0:e1], hi[e0:e1], (hp[lo:hi_ + 1] - e0).astype(np.int32), per_core))
     os.environ["OMP_NUM_THREADS"] = "1"
     ctxm = mp.get_context("fork")
     with ctxm.Pool(cores, initializer=_w_init, initargs=(G.data, G.indices, G.indptr, names)) as pool:
         def step():
+            if wl != "plaid":  # every block through the whole scorer (its global scalars taken per block)
+                pool.map(_w_whole, [(wl,) + b for b in blocks], chunksize=1)
+                return
             res = pool.map(_w_phase1, blocks, chunksize=1)
             smin = min(r[0] for r in res)
             use_nz = smin == 0
@@ -372,11 +557,14 @@ def run_reference(a):
     v = S_SETS * float(n) * a.steps / dt
     sample = (f"{n} cells ({per_core}/core) x {S_SETS} sets per step; oracle port of R/plaid.R (scipy Gustavson product, "
               f"densify, per-column medians, sweep), column-sharded over {cores} processes")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    if wl != "plaid":
+        sample = (f"{n} columns ({per_core}/core) x {S_SETS} sets per step; oracle port of {_oracle_fn(wl).__name__} (R/plaid.R), every "
+                  f"core scores its own column block through the whole function, {cores} processes")
+    line = {"impl": "reference", "metric": METRIC if wl.startswith("plaid") else METRIC.replace("plaid()", f"replaid.{wl}()"), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4-shard plaid(): sparse dgCMatrix {P_GENES} genes x cells (~7% nnz), {S_SETS} gene sets, "
-                                   f"stats=mean, normalize=TRUE", "genes": P_GENES, "gene_sets": S_SETS,
+            "config": {"workload": f"{wl}: {WORKLOADS[wl][2]}; {P_GENES} genes, {S_SETS} gene sets; BASELINE.json {WORKLOADS[wl][3]}",
+                       "genes": P_GENES, "gene_sets": S_SETS,
                        "cells_per_step": n},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -104,11 +104,16 @@ class Context:
         """Register matG (genes x sets, scipy sparse).  Values only matter as zero / non-zero."""
         if G is getattr(self, "_glast", None):  # same object as last time: nothing to do (the caller must
             return                               # not mutate a registered matrix in place)
-        self._glast = G
+        G0 = G
         G = sp.csc_matrix(G)
-        G.sort_indices()
+        if G.nnz >= 2 ** 31 or G.shape[0] >= 2 ** 31:
+            raise ValueError("matG has 2^31 or more stored entries / rows (dgCMatrix slots are int32)")
+        if not G.has_sorted_indices:
+            G = G.copy()  # never reorder the caller's arrays
+            G.sort_indices()
         key = (G.shape, G.nnz, hash(G.indptr.tobytes()), hash(G.indices.tobytes()), hash(G.data.tobytes()))
         if key == self._gkey:
+            self._glast = G0
             return
         gp = np.ascontiguousarray(G.indptr, dtype=np.int32)
         gi = np.ascontiguousarray(G.indices, dtype=np.int32)
@@ -116,6 +121,7 @@ class Context:
         self.check(self.lib.plaidgpu_set_genesets(self.h, G.shape[0], G.shape[1], gp.ctypes.data,
                                                   gi.ctypes.data, gx.ctypes.data))
         self._gkey = key
+        self._glast = G0  # only after the C call succeeded: a failed registration is retried
 
     def launch_count(self) -> int:
         return int(self.lib.plaidgpu_launch_count(self.h))
@@ -184,7 +190,11 @@ def _matrix_struct(m, keep: list) -> L.Matrix:
         return M
     if sp is not None and sp.issparse(m):
         m = sp.csc_matrix(m)
-        m.sort_indices()
+        if m.nnz >= 2 ** 31 or m.shape[0] >= 2 ** 31:  # dgCMatrix slots are int32; scipy switches to int64 silently
+            raise ValueError("X has 2^31 or more stored entries / rows: split the columns into shards (plaid_b200.sharded)")
+        if not m.has_sorted_indices:
+            m = m.copy()  # csc_matrix(m) shares buffers with a CSC input: never reorder the caller's arrays
+            m.sort_indices()
         p = np.ascontiguousarray(m.indptr, dtype=np.int32)
         i = np.ascontiguousarray(m.indices, dtype=np.int32)
         x = np.ascontiguousarray(m.data, dtype=np.float64)

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -67,11 +68,27 @@ class CopyPool {
     d_ = static_cast<char*>(dst);
     s_ = static_cast<const char*>(src);
     n_ = bytes;
+    fn_ = nullptr;
     pending_ = (int)th_.size();
     ++gen_;
     cv_work_.notify_all();
     cv_done_.wait(lk, [this] { return pending_ == 0; });
   }
+  // fn(part, parts) on every worker thread, blocking
+  void run(const std::function<void(int, int)>& fn) {
+    if (th_.empty()) {
+      fn(0, 1);
+      return;
+    }
+    std::unique_lock<std::mutex> lk(m_);
+    fn_ = &fn;
+    pending_ = (int)th_.size();
+    ++gen_;
+    cv_work_.notify_all();
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+  int threads() const { return (int)th_.size(); }
 
  private:
   void run(int i) {
@@ -86,8 +103,10 @@ class CopyPool {
       const size_t lo = std::min(n_, per * (size_t)i), hi = std::min(n_, lo + per);
       char* d = d_;
       const char* s = s_;
+      const std::function<void(int, int)>* fn = fn_;
       lk.unlock();
-      if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+      if (fn) (*fn)(i, (int)parts);
+      else if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
       lk.lock();
       if (--pending_ == 0) cv_done_.notify_all();
     }
@@ -98,6 +117,7 @@ class CopyPool {
   char* d_ = nullptr;
   const char* s_ = nullptr;
   size_t n_ = 0;
+  const std::function<void(int, int)>* fn_ = nullptr;
   int gen_ = 0, pending_ = 0;
   bool stop_ = false;
 };
@@ -124,6 +144,12 @@ struct plaidgpu_ctx {
   size_t ring_bytes = 0;
   cudaEvent_t ev_ring[RING] = {};
   CopyPool* pool = nullptr;
+  // early shipping (pinned host output): column chunks of the RAW scores cross PCIe while later chunks are still
+  // being scored; plaidgpu_score_finish fixes those columns up on the host (same arithmetic as k_fixup)
+  double* early_out = nullptr;
+  int64_t early_cols = 0;
+  cudaEvent_t ev_early = nullptr, ev_d2h[2] = {};
+  double d2h_ms_per_col = 0.0, comp_ms_per_col = 0.0;  // measured by the previous call: sizes the early part
   std::string err;
   int64_t launches = 0;
   double ms[4] = {0, 0, 0, 0};  // 0 score, 1 colstats, 2 fixup, 3 rank
@@ -168,7 +194,7 @@ struct plaidgpu_ctx {
   const double* xx = nullptr;
   DevBuf b_xp, b_xi, b_xx, b_rank, b_r0, b_colmax, b_raw, b_med_all, b_med_nz, b_colmin, b_scal, b_i32, b_dense, b_rowa, b_rowb, b_fail, b_list, b_ci, b_cx, b_ce;
   double* raw = nullptr;  // device S x N raw scores (caller's buffer or b_raw)
-  bool need_norm = false;
+  bool need_norm = false, need_norm_hint = false;
   // which column medians of the raw scores are known (the statistics pass computes only the one the
   // shard's own minimum says normalize_medians will use; the other is computed on demand)
   bool have_all = false, have_nz = false, raw_valid = false, want_both = false;
@@ -262,9 +288,10 @@ int build_plan(plaidgpu_ctx* c, int32_t P, const int32_t* rowmap, int32_t tile_h
               [&](int32_t x, int32_t y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
     int32_t k = 0;
     if (tc_on) {
-      // a row costs the tensor-core pass the same whatever its degree, the scatter pass in proportion to it:
-      // rows in at least ~0.55 % of the sets go to the block (3,072 rows on the 30k-set benchmark collection)
-      double frac = 0.0055;
+      // a row costs the tensor-core pass the same whatever its degree, the tail pass in proportion to it (degree x
+      // ceil(entries per 1,056-cell tile / 32)): rows in at least ~0.75 % of the sets go to the block (about 1,800
+      // rows on the 30k-set benchmark collection; measured optimum 1,536 - 2,048)
+      double frac = 0.0075;
       if (const char* e = getenv("PLAIDGPU_TC_DEGFRAC")) frac = atof(e);
       const uint32_t thr = (uint32_t)std::max(32.0, ceil(frac * (double)S));
       while (k < P && deg[order[k]] >= thr) ++k;
@@ -637,6 +664,24 @@ int max_col_nnz(plaidgpu_ctx* c, int32_t* out) {
   return PLAIDGPU_OK;
 }
 
+// one column of the fix-up on the host: out = alpha * (x + ((-med) + c)) [+ beta_s], every operation rounded on its own
+// like the device kernels (k_fixup / k_fixup_flat are written with __dadd_rn / __dmul_rn, this file is compiled
+// without FMA contraction for the host)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+void host_fixup_column(double* col, int32_t S, double med, bool has_med, double c, double alpha, const double* beta) {
+  const double shift = (has_med ? -med : 0.0) + c;
+  if (beta) {
+    for (int32_t s = 0; s < S; ++s) {
+      const double t = alpha * (col[s] + shift);
+      col[s] = t + beta[s];
+    }
+  } else {
+    for (int32_t s = 0; s < S; ++s) col[s] = alpha * (col[s] + shift);
+  }
+}
+#pragma GCC pop_options
+
 double r_mean(const double* v, int64_t n) {  // base::mean(na.rm = TRUE): long double, one refinement
   long double s = 0.0L;
   int64_t m = 0;
@@ -679,7 +724,7 @@ void plaidgpu_default_opts(plaidgpu_opts* o) {
   o->matg_full_colsums = nullptr;
 }
 
-int plaidgpu_init(int device, plaidgpu_ctx** out) {
+int plaidgpu_init(int device, plaidgpu_ctx** out) try {
   if (!out) return PLAIDGPU_ERR_ARG;
   *out = nullptr;
   int n = 0;
@@ -698,8 +743,14 @@ int plaidgpu_init(int device, plaidgpu_ctx** out) {
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   for (auto& ev : c->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming);
+  for (auto& ev : c->ev_d2h) cudaEventCreate(&ev);
   *out = c;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 void plaidgpu_destroy(plaidgpu_ctx* c) {
@@ -714,6 +765,8 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_ring) if (ev) cudaEventDestroy(ev);
+  if (c->ev_early) cudaEventDestroy(c->ev_early);
+  for (auto& ev : c->ev_d2h) if (ev) cudaEventDestroy(ev);
   for (auto& r : c->ring) if (r) cudaFreeHost(r);
   delete c->pool;
   cudaStreamDestroy(c->stream);
@@ -730,7 +783,7 @@ double plaidgpu_last_kernel_ms(const plaidgpu_ctx* c, int which) {
 void* plaidgpu_stream(const plaidgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int plaidgpu_plan_info(const plaidgpu_ctx* c, int32_t* tile_sets, int32_t* n_tiles, int64_t* nnz_mapped,
-                       int32_t* warps_per_cta, int32_t* ctas, int32_t* gather_block, int32_t* gather_blocks) {
+                       int32_t* warps_per_cta, int32_t* ctas, int32_t* gather_block, int32_t* gather_blocks) try {
   if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
   if (tile_sets) *tile_sets = c->Ts;
   if (n_tiles) *n_tiles = c->T;
@@ -740,25 +793,37 @@ int plaidgpu_plan_info(const plaidgpu_ctx* c, int32_t* tile_sets, int32_t* n_til
   if (gather_block) *gather_block = c->gK;
   if (gather_blocks) *gather_blocks = c->gblocks;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_tc_info(const plaidgpu_ctx* c, int32_t* block_rows, int32_t* padded_rows, int32_t* slices) {
+int plaidgpu_tc_info(const plaidgpu_ctx* c, int32_t* block_rows, int32_t* padded_rows, int32_t* slices) try {
   if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
   if (block_rows) *block_rows = c->tcK > 0 ? c->tc_rows : 0;
   if (padded_rows) *padded_rows = c->tcK;
   if (slices) *slices = c->tc_slices;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_tail_info(const plaidgpu_ctx* c, int32_t* tail_rows, int32_t* tile_cells) {
+int plaidgpu_tail_info(const plaidgpu_ctx* c, int32_t* tail_rows, int32_t* tile_cells) try {
   if (!c || !c->plan_ok) return PLAIDGPU_ERR_STATE;
   if (tail_rows) *tail_rows = c->tail_on ? c->Pt : 0;
   if (tile_cells) *tile_cells = tail_tile_cells();
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int plaidgpu_set_genesets(plaidgpu_ctx* c, int32_t P_G, int32_t S, const int32_t* Gp, const int32_t* Gi,
-                          const double* Gx) {
+                          const double* Gx) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (P_G <= 0 || S <= 0 || !Gp || (!Gi && Gp[S] > 0)) return fail(c, PLAIDGPU_ERR_ARG, "bad gene-set matrix");
   // the same pattern again (an R caller re-registers matG on every call): keep the plan
@@ -786,11 +851,15 @@ int plaidgpu_set_genesets(plaidgpu_ctx* c, int32_t P_G, int32_t S, const int32_t
   }
   c->have_g = true;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 // -----------------------------------------------------------------------------------------
 int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap,
-                         const plaidgpu_opts* opts, plaidgpu_scalars* local) {
+                         const plaidgpu_opts* opts, plaidgpu_scalars* local) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !rowmap || !opts || !local) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_set_genesets has not been called");
@@ -918,9 +987,13 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   }
   c->in_call = true;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out) {
+int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!scal) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->in_call) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_begin has not been called");
@@ -993,6 +1066,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       return fail(c, PLAIDGPU_ERR_ARG, "unknown scorer");
   }
   p.inv = mean ? c->d_inv_mean.as<double>() : c->d_inv_one.as<double>();
+  c->need_norm_hint = c->need_norm || o.scorer == PLAIDGPU_UCELL;
   if (is_rank_scorer(o.scorer) || o.scorer == PLAIDGPU_GSVA) {
     if (c->dense) {
       // dense input: transform the dense rank matrix in place, then plain product
@@ -1015,6 +1089,22 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     c->raw = c->b_raw.as<double>();
   }
   p.out = c->raw;
+  // early shipping: with a pinned host destination, finished column chunks start crossing PCIe at once
+  c->early_out = nullptr;
+  c->early_cols = 0;
+  int64_t early_limit = 0;
+  if (o.out_location == PLAIDGPU_HOST && out && total > 0 && !getenv("PLAIDGPU_NO_EARLY") && !is_pageable(out)) {
+    c->early_out = out;
+    double frac = 1.0;  // no normalisation: every chunk is final as soon as it is scored
+    if (c->need_norm_hint) {
+      // normalised scores need mean(medians) of ALL columns: only as many chunks go out raw as PCIe can move
+      // while the rest is scored (rates of the previous call; a conservative guess for the first one)
+      frac = (c->d2h_ms_per_col > 0.0 && c->comp_ms_per_col > 0.0) ? 1.1 * c->comp_ms_per_col / c->d2h_ms_per_col : 0.12;
+      if (const char* e = getenv("PLAIDGPU_EARLY_FRAC")) frac = atof(e);
+      frac = std::min(0.6, std::max(0.0, frac));
+    }
+    early_limit = (int64_t)(frac * (double)c->N);
+  }
 
   if (colnorm) {  // replaid.scse: column sums / means of |X| over ALL rows of X (R/plaid.R:176,181)
     CK(c->d_colscale.reserve(std::max<int64_t>(c->N, 1) * sizeof(double)));
@@ -1050,7 +1140,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     const int TC_ = tail_tile_cells();
     int64_t chunk = std::max<int64_t>(ct, ((int64_t)(4ll << 30) / ((int64_t)c->tcK * sl)) / ct * ct);
     if (tail) {
-      int64_t tiles = std::max<int64_t>(1, (int64_t)(4ll << 30) / ((int64_t)c->S * TC_ * 8));
+      int64_t tiles = std::min<int64_t>(8, std::max<int64_t>(1, (int64_t)(4ll << 30) / ((int64_t)c->S * TC_ * 8)));
       if (const char* e = getenv("PLAIDGPU_TAIL_TILES")) tiles = std::max(1, atoi(e));
       chunk = std::max<int64_t>(TC_, std::min<int64_t>(chunk / TC_, tiles) * TC_);
       if (chunk > c->N) chunk = (c->N + TC_ - 1) / TC_ * TC_;
@@ -1122,6 +1212,14 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       t.colfb = (tail && p.mode >= XF_SING) ? c->b_colfb.as<double>() + j0 : nullptr;
       CK(launch_tc_score(t, c->b_tcB.as<signed char>(), c->tcK, sl, c->stream));
       c->launches += 2;
+      if (c->early_out && t.final && j0 + nj <= early_limit) {
+        CK(cudaEventRecord(c->ev_chunk[0], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[0], 0));
+        CK(cudaMemcpyAsync(c->early_out + j0 * (int64_t)c->S, c->raw + j0 * (int64_t)c->S, (size_t)nj * c->S * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(c->ev_early, c->copy_stream));
+        c->early_cols = j0 + nj;
+      }
     }
     compacted = !c->dense && c->nnz > 0;
   }
@@ -1209,6 +1307,15 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
+  if (c->early_cols > 0) {
+    // a non-finite entry sent the call through the fp64 passes AFTER chunks had left: ship everything again
+    int flag = 0;
+    CK(cudaMemcpy(&flag, c->b_tcflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+      CK(cudaStreamSynchronize(c->copy_stream));
+      c->early_cols = 0;
+    }
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->ms[0] = ms;
@@ -1221,9 +1328,13 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   }
   c->computed = true;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_get_col_medians(plaidgpu_ctx* c, double* med_all, double* med_nz) {
+int plaidgpu_get_col_medians(plaidgpu_ctx* c, double* med_all, double* med_nz) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!c->computed || !c->need_norm) return fail(c, PLAIDGPU_ERR_STATE, "no medians: run plaidgpu_score_compute with normalisation");
   if (med_all) {
@@ -1237,25 +1348,37 @@ int plaidgpu_get_col_medians(plaidgpu_ctx* c, double* med_all, double* med_nz) {
     memcpy(med_nz, c->h_med_nz.data(), (size_t)c->N * sizeof(double));
   }
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_get_col_medians_for(plaidgpu_ctx* c, int ignore_zero, double* med) {
+int plaidgpu_get_col_medians_for(plaidgpu_ctx* c, int ignore_zero, double* med) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!med && c->N > 0) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   return ignore_zero ? plaidgpu_get_col_medians(c, nullptr, med) : plaidgpu_get_col_medians(c, med, nullptr);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double* med_all, const double* med_nz,
-                             int64_t N_total, plaidgpu_scalars* scal) {
+                             int64_t N_total, plaidgpu_scalars* scal) try {
   if (!scal || !med_all || !med_nz || N_total < 0) return PLAIDGPU_ERR_ARG;
   const int iz = ignore_zero_opt < 0 ? (score_min == 0.0 ? 1 : 0) : (ignore_zero_opt != 0);  // R/plaid.R:556-557
   scal->ignore_zero = iz;
   scal->score_min = score_min;
   scal->med_mean = r_mean(iz ? med_nz : med_all, N_total);  // R/plaid.R:572
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double* out) {
+int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!scal || (!out && c->N > 0)) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->computed) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_compute has not been called");
@@ -1315,7 +1438,7 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
         c->ring_bytes = want;
       }
       if (!c->pool) {
-        int nt = (int)std::min<unsigned>(8, std::max(2u, std::thread::hardware_concurrency() / 2));
+        int nt = (int)std::min<unsigned>(12, std::max(2u, std::thread::hardware_concurrency() * 3 / 4));
         if (const char* e = getenv("PLAIDGPU_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
         c->pool = new CopyPool(nt);
       }
@@ -1348,9 +1471,49 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
       c->ms[2] = msr;
       return PLAIDGPU_OK;
     }
+    // columns [0, E) already left as RAW scores while the rest was being scored (plaidgpu_score_compute): a helper
+    // thread fixes them up in the caller's matrix — the arithmetic of k_fixup, operation by operation — while the
+    // remaining blocks are fixed up on the device and follow over PCIe
+    const int64_t E = (c->early_out == out) ? std::min<int64_t>(c->early_cols, N) : 0;
+    c->early_out = nullptr;
+    c->early_cols = 0;
+    std::thread patcher;
+    struct Joiner {
+      std::thread& t;
+      ~Joiner() {
+        if (t.joinable()) t.join();
+      }
+    } joiner{patcher};  // also on the error returns below
+    std::vector<double> hbeta;
+    if (E > 0 && fix) {
+      if (beta) {
+        hbeta.resize((size_t)S);
+        const double* gs = o.matg_full_colsums ? o.matg_full_colsums : c->g_colsums.data();
+        for (int32_t s = 0; s < S; ++s) hbeta[s] = 1.0 + (gs[s] + 1.0) / (2.0 * o.rmax);
+      }
+      if (!c->pool) {
+        int nt = (int)std::min<unsigned>(8, std::max(2u, std::thread::hardware_concurrency() / 2));
+        if (const char* e = getenv("PLAIDGPU_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+        c->pool = new CopyPool(nt);
+      }
+      const double* hm = med ? (scal->ignore_zero ? c->h_med_nz.data() : c->h_med_all.data()) : nullptr;
+      const double* hb = beta ? hbeta.data() : nullptr;
+      cudaEvent_t evE = c->ev_early;
+      CopyPool* pool = c->pool;
+      const int dev = c->device;
+      patcher = std::thread([=] {
+        cudaSetDevice(dev);
+        cudaEventSynchronize(evE);
+        pool->run([=](int part, int parts) {
+          const int64_t lo = E * part / parts, hi = E * (part + 1) / parts;
+          for (int64_t j = lo; j < hi; ++j) host_fixup_column(out + j * (int64_t)S, S, hm ? hm[j] : 0.0, hm != nullptr, cc, alpha, hb);
+        });
+      });
+    }
     int64_t chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / ((int64_t)S * 8));
     int k = 0;
-    for (int64_t j0 = 0; j0 < N; j0 += chunk, ++k) {
+    bool first = true;
+    for (int64_t j0 = E; j0 < N; j0 += chunk, ++k) {
       const int64_t j1 = std::min<int64_t>(N, j0 + chunk);
       if (fix) {
         CK(launch_fixup(c->raw, c->raw, S, S, j0, j1, med, cc, alpha, beta, c->stream));
@@ -1358,17 +1521,34 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
       }
       CK(cudaEventRecord(c->ev_chunk[k & 1], c->stream));
       CK(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[k & 1], 0));
+      if (first) CK(cudaEventRecord(c->ev_d2h[0], c->copy_stream));
+      first = false;
       CK(cudaMemcpyAsync(out + j0 * S, c->raw + j0 * S, (size_t)(j1 - j0) * S * sizeof(double),
                          cudaMemcpyDeviceToHost, c->copy_stream));
     }
+    if (!first) CK(cudaEventRecord(c->ev_d2h[1], c->copy_stream));
     CK(cudaEventRecord(c->ev[5], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaStreamSynchronize(c->copy_stream));
+    cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);
+    if (patcher.joinable()) patcher.join();
+    CK(e1);
+    CK(e2);
+    if (!first && N - E >= 64) {  // rates for the next call's early part
+      float dms = 0.f;
+      if (cudaEventElapsedTime(&dms, c->ev_d2h[0], c->ev_d2h[1]) == cudaSuccess && dms > 0.f) {
+        c->d2h_ms_per_col = (double)dms / (double)(N - E);
+        c->comp_ms_per_col = (c->ms[0] + c->ms[1]) / (double)N;
+      }
+    }
   }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
   c->ms[2] = ms;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 // Column-chunked scoring for host input / host output when the S x N result does not fit the device
@@ -1471,7 +1651,7 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
 }
 
 int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
-                           const char* path, int format) {
+                           const char* path, int format) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !opts || !path) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "no gene sets registered");
@@ -1520,10 +1700,14 @@ int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int3
   cudaFreeHost(stage);
   if (fclose(f) != 0 && !rc) rc = fail(c, PLAIDGPU_ERR_ARG, "closing the output file failed");
   return rc;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
-                   double* out) {
+                   double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !opts) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   // host in / host out larger than the device can hold -> column chunks
@@ -1556,6 +1740,10 @@ int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* row
     if (rc) return fail(c, rc, "combine_medians failed");
   }
   return plaidgpu_score_finish(c, &s, out);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1584,7 +1772,7 @@ struct ShardBarrier {
 }  // namespace
 
 int plaidgpu_score_multi(plaidgpu_ctx* const* ctxs, int n, const plaidgpu_matrix* X, const int32_t* rowmap,
-                         const plaidgpu_opts* opts, double* out) {
+                         const plaidgpu_opts* opts, double* out) try {
   if (!ctxs || n <= 0 || !ctxs[0]) return PLAIDGPU_ERR_ARG;
   plaidgpu_ctx* c = ctxs[0];
   if (!X || !rowmap || !opts) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
@@ -1671,7 +1859,7 @@ int plaidgpu_score_multi(plaidgpu_ctx* const* ctxs, int n, const plaidgpu_matrix
         s.x_max = fmax(s.x_max, loc[k].x_max);
         s.rank_max = fmax(s.rank_max, loc[k].rank_max);
       }
-      rc[r] = plaidgpu_score_compute(cr, &s, nullptr);
+      rc[r] = plaidgpu_score_compute(cr, &s, out + lo[r] * (int64_t)S);
       loc[r].score_min = s.score_min;
       bar.wait();
       if (failed()) return;
@@ -1706,10 +1894,14 @@ int plaidgpu_score_multi(plaidgpu_ctx* const* ctxs, int n, const plaidgpu_matrix
   } catch (...) {
     return fail(c, PLAIDGPU_ERR_ARG, "unexpected failure in plaidgpu_score_multi");
   }
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t* rowmap, const double* colscale,
-                       int out_location, double* out) {
+                       int out_location, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!Y || !rowmap) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_set_genesets has not been called");
@@ -1735,9 +1927,13 @@ int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t*
   }
   if (rc) return rc;
   return plaidgpu_score_finish(c, &s, out);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double* mean, double* out) {
+int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double* mean, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   CK(cudaSetDevice(c->device));
@@ -1748,9 +1944,13 @@ int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double
   rc = make_dense(c);
   if (rc) return rc;
   return row_moments(c, mean, out);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_row_ecdf(plaidgpu_ctx* c, double* x, int64_t N, int32_t rows, int location) {
+int plaidgpu_row_ecdf(plaidgpu_ctx* c, double* x, int64_t N, int32_t rows, int location) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!x && N > 0 && rows > 0) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (N < 0 || rows < 0 || N > 0x7fffffff) return fail(c, PLAIDGPU_ERR_ARG, "bad dimensions for row ecdf");
@@ -1776,11 +1976,15 @@ int plaidgpu_row_ecdf(plaidgpu_ctx* c, double* x, int64_t N, int32_t rows, int l
   cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
   c->ms[3] = ms;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 // -----------------------------------------------------------------------------------------
 int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int is_signed, int keep_zero,
-                      int out_location, double* out) {
+                      int out_location, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (ties < PLAIDGPU_TIES_AVERAGE || ties > PLAIDGPU_TIES_MAX) return fail(c, PLAIDGPU_ERR_ARG, "unsupported ties.method");
@@ -1839,10 +2043,14 @@ int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int i
   cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
   c->ms[3] = ms;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int plaidgpu_group_moments(plaidgpu_ctx* c, const double* x, int32_t S, int64_t N, const int32_t* y, int location,
-                           double* out) {
+                           double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (S <= 0 || N < 0 || !out || (N > 0 && (!x || !y))) return fail(c, PLAIDGPU_ERR_ARG, "bad argument");
   CK(cudaSetDevice(c->device));
@@ -1864,11 +2072,15 @@ int plaidgpu_group_moments(plaidgpu_ctx* c, const double* x, int32_t S, int64_t 
   CK(cudaMemcpyAsync(out, c->b_rowb.p, (size_t)4 * S * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 // -----------------------------------------------------------------------------------------
 int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int64_t N, int ignore_zero,
-                               int location, double* out) {
+                               int location, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (S <= 0 || N < 0 || (N > 0 && (!x || !out))) return fail(c, PLAIDGPU_ERR_ARG, "bad argument");
   CK(cudaSetDevice(c->device));
@@ -1925,6 +2137,10 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int6
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
   c->ms[2] = ms;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 }  // extern "C"

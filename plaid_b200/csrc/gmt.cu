@@ -106,7 +106,7 @@ int build(std::vector<RawSet>& raw, plaidgpu_gmt* g) {
 
 extern "C" {
 
-int plaidgpu_gmt_from_buffer(const char* text, int64_t len, plaidgpu_gmt** out) {
+int plaidgpu_gmt_from_buffer(const char* text, int64_t len, plaidgpu_gmt** out) try {
   if (!text || len < 0 || !out) return PLAIDGPU_ERR_ARG;
   *out = nullptr;
   plaidgpu_gmt* g = new (std::nothrow) plaidgpu_gmt();
@@ -120,9 +120,13 @@ int plaidgpu_gmt_from_buffer(const char* text, int64_t len, plaidgpu_gmt** out) 
   }
   *out = g;
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_gmt_read(const char* path, plaidgpu_gmt** out) {
+int plaidgpu_gmt_read(const char* path, plaidgpu_gmt** out) try {
   if (!path || !out) return PLAIDGPU_ERR_ARG;
   FILE* f = fopen(path, "rb");
   if (!f) return PLAIDGPU_ERR_ARG;
@@ -132,6 +136,10 @@ int plaidgpu_gmt_read(const char* path, plaidgpu_gmt** out) {
   while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.append(tmp, n);
   fclose(f);
   return plaidgpu_gmt_from_buffer(buf.data(), (int64_t)buf.size(), out);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 void plaidgpu_gmt_free(plaidgpu_gmt* g) { delete g; }
@@ -144,13 +152,17 @@ const char* plaidgpu_gmt_set_name(const plaidgpu_gmt* g, int64_t k) {
 const char* plaidgpu_gmt_gene_name(const plaidgpu_gmt* g, int64_t k) {
   return (g && k >= 0 && k < (int64_t)g->gene_names.size()) ? g->gene_names[(size_t)k].c_str() : nullptr;
 }
-int plaidgpu_gmt_csc(const plaidgpu_gmt* g, int32_t* Gp, int32_t* Gi) {
+int plaidgpu_gmt_csc(const plaidgpu_gmt* g, int32_t* Gp, int32_t* Gi) try {
   if (!g || !Gp || (!Gi && !g->Gi.empty())) return PLAIDGPU_ERR_ARG;
   memcpy(Gp, g->Gp.data(), g->Gp.size() * sizeof(int32_t));
   if (!g->Gi.empty()) memcpy(Gi, g->Gi.data(), g->Gi.size() * sizeof(int32_t));
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
-int plaidgpu_gmt_rowmap(const plaidgpu_gmt* g, const char* const* xnames, int32_t P, int32_t* rowmap) {
+int plaidgpu_gmt_rowmap(const plaidgpu_gmt* g, const char* const* xnames, int32_t P, int32_t* rowmap) try {
   if (!g || !xnames || !rowmap || P < 0) return PLAIDGPU_ERR_ARG;
   std::unordered_map<std::string, char> seen;
   seen.reserve((size_t)P * 2);
@@ -163,6 +175,10 @@ int plaidgpu_gmt_rowmap(const plaidgpu_gmt* g, const char* const* xnames, int32_
     if (it != g->gene_pos.end()) rowmap[r] = it->second;
   }
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 }  // extern "C"

@@ -128,7 +128,10 @@ void coo_to_csc(int32_t P, int64_t N, const std::vector<const CooPart*>& parts, 
   m->N = N;
   std::vector<int64_t> cnt((size_t)N + 1, 0);
   for (const CooPart* c : parts)
-    for (int64_t col : c->ci) ++cnt[(size_t)col + 1];
+    for (int64_t col : c->ci) {
+      if (col < 0 || col >= N) abort();  // callers range-check every column index: never reached
+      ++cnt[(size_t)col + 1];
+    }
   for (int64_t j = 0; j < N; ++j) cnt[(size_t)j + 1] += cnt[(size_t)j];
   std::vector<int32_t> rows(nz);
   std::vector<double> vals(nz);
@@ -252,6 +255,7 @@ int parse_mtx(const std::string& buf, plaidgpu_spmat* m) {
   int64_t P = 0, N = 0, nz = 0;
   if (!parse_i64(s, e, &P) || !parse_i64(s, e, &N) || !parse_i64(s, e, &nz)) return io_fail("Matrix Market: bad size line");
   if (P <= 0 || P > 0x7fffffff || N < 0 || nz < 0) return io_fail("Matrix Market: dimensions out of range");
+  if (symmetric && P != N) return io_fail("Matrix Market: a symmetric matrix must be square");  // mirrored entries would leave the matrix
   le = line_end(s);
   s = le < e ? le + 1 : e;
   // the entry lines are independent: parse them on several host threads, one contiguous slice of the
@@ -302,6 +306,10 @@ int parse_mtx(const std::string& buf, plaidgpu_spmat* m) {
       w->ci.push_back(c - 1);
       w->v.push_back(val);
       if (symmetric && r != c) {
+        if (c > P || r > N) {  // cannot happen for a square matrix; kept as a guard on the mirrored index
+          w->err = "index out of range";
+          return;
+        }
         w->ri.push_back((int32_t)(c - 1));
         w->ci.push_back(r - 1);
         w->v.push_back(val);
@@ -512,6 +520,7 @@ struct XdrReader {
           const double cnt = real_state ? state->reals[0] : state->ints[0];
           const double start = real_state ? state->reals[1] : state->ints[1];
           const double inc = real_state ? state->reals[2] : state->ints[2];
+          if (!(cnt >= 0.0) || cnt > 2147483647.0) return fail("compact sequence length out of range");  // a dgCMatrix slot never exceeds 2^31-1
           if (cls == "compact_intseq") {
             s->type = 13;
             for (int64_t k = 0; k < (int64_t)cnt; ++k) s->ints.push_back((int32_t)(start + inc * (double)k));
@@ -541,11 +550,13 @@ struct XdrReader {
     s->type = type;
     if (type == 10 || type == 13) {
       const int64_t cnt = len();
+      if (cnt < 0 || (uint64_t)cnt > (uint64_t)(n - o) / 4) return fail("unexpected end of the stream (a vector is longer than what is left)");
       if (!need((size_t)cnt * 4)) return nil();
       s->ints.resize((size_t)cnt);
       for (int64_t k = 0; k < cnt; ++k) s->ints[(size_t)k] = i32();
     } else if (type == 14) {
       const int64_t cnt = len();
+      if (cnt < 0 || (uint64_t)cnt > (uint64_t)(n - o) / 8) return fail("unexpected end of the stream (a vector is longer than what is left)");
       if (!need((size_t)cnt * 8)) return nil();
       s->reals.resize((size_t)cnt);
       for (int64_t k = 0; k < cnt; ++k) s->reals[(size_t)k] = f64();
@@ -604,7 +615,7 @@ extern "C" {
 
 const char* plaidgpu_io_error(void) { return g_io_err.c_str(); }
 
-int plaidgpu_spmat_read_mtx(const char* path, plaidgpu_spmat** out) {
+int plaidgpu_spmat_read_mtx(const char* path, plaidgpu_spmat** out) try {
   if (!path || !out) return io_fail("null argument");
   std::string buf;
   if (!load(path, buf)) return PLAIDGPU_ERR_ARG;
@@ -613,9 +624,13 @@ int plaidgpu_spmat_read_mtx(const char* path, plaidgpu_spmat** out) {
   if (rc) return rc;
   *out = m.release();
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_spmat_read_10x(const char* dir, plaidgpu_spmat** out) {
+int plaidgpu_spmat_read_10x(const char* dir, plaidgpu_spmat** out) try {
   if (!dir || !out) return io_fail("null argument");
   const std::string d(dir);
   auto pick = [&](std::initializer_list<const char*> names) -> std::string {
@@ -644,9 +659,13 @@ int plaidgpu_spmat_read_10x(const char* dir, plaidgpu_spmat** out) {
   }
   *out = hold.release();
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
-int plaidgpu_spmat_read_rda(const char* path, const char* object, plaidgpu_spmat** out) {
+int plaidgpu_spmat_read_rda(const char* path, const char* object, plaidgpu_spmat** out) try {
   if (!path || !out) return io_fail("null argument");
   std::string buf;
   if (!load(path, buf)) return PLAIDGPU_ERR_ARG;
@@ -693,11 +712,15 @@ int plaidgpu_spmat_read_rda(const char* path, const char* object, plaidgpu_spmat
   if (rc) return rc;
   *out = m.release();
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 void plaidgpu_spmat_free(plaidgpu_spmat* m) { delete m; }
 
-int plaidgpu_spmat_view(const plaidgpu_spmat* m, plaidgpu_matrix* M) {
+int plaidgpu_spmat_view(const plaidgpu_spmat* m, plaidgpu_matrix* M) try {
   if (!m || !M) return PLAIDGPU_ERR_ARG;
   memset(M, 0, sizeof(*M));
   M->kind = PLAIDGPU_CSC;
@@ -708,6 +731,10 @@ int plaidgpu_spmat_view(const plaidgpu_spmat* m, plaidgpu_matrix* M) {
   M->i = m->i.data();
   M->x = m->x.data();
   return PLAIDGPU_OK;
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
 }
 
 int64_t plaidgpu_spmat_nnz(const plaidgpu_spmat* m) { return m ? (int64_t)m->i.size() : 0; }

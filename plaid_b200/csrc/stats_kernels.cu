@@ -674,23 +674,23 @@ __global__ void __launch_bounds__(256) k_fixup(const double* __restrict__ x, dou
       double2* __restrict__ o2 = reinterpret_cast<double2*>(oi);
       for (int l = threadIdx.x; l < S2; l += blockDim.x) {
         double2 v = __ldcs(x2 + l);
-        v.x = alpha * (v.x + shift);
-        v.y = alpha * (v.y + shift);
+        v.x = __dmul_rn(alpha, __dadd_rn(v.x, shift));  // no FMA: the host applies the same fix-up to early-shipped columns
+        v.y = __dmul_rn(alpha, __dadd_rn(v.y, shift));
         if (beta) {
-          v.x += beta[2 * l];
-          v.y += beta[2 * l + 1];
+          v.x = __dadd_rn(v.x, beta[2 * l]);
+          v.y = __dadd_rn(v.y, beta[2 * l + 1]);
         }
         __stcs(o2 + l, v);
       }
       if ((S & 1) && threadIdx.x == 0) {
-        double v = alpha * (xi[S - 1] + shift);
-        if (beta) v += beta[S - 1];
+        double v = __dmul_rn(alpha, __dadd_rn(xi[S - 1], shift));
+        if (beta) v = __dadd_rn(v, beta[S - 1]);
         oi[S - 1] = v;
       }
     } else {
       for (int l = threadIdx.x; l < S; l += blockDim.x) {
-        double v = alpha * (xi[l] + shift);
-        if (beta) v += beta[l];
+        double v = __dmul_rn(alpha, __dadd_rn(xi[l], shift));
+        if (beta) v = __dadd_rn(v, beta[l]);
         oi[l] = v;
       }
     }
@@ -720,12 +720,12 @@ __global__ void __launch_bounds__(256) k_fixup_flat(const double* __restrict__ x
       double2 v = __ldcs(x2 + (e >> 1));
       const bool second = e >= bound;             // S is even: both halves of a pair lie in one column
       const double shift = second ? sb : sa;
-      v.x = alpha * (v.x + shift);
-      v.y = alpha * (v.y + shift);
+      v.x = __dmul_rn(alpha, __dadd_rn(v.x, shift));
+      v.y = __dmul_rn(alpha, __dadd_rn(v.y, shift));
       if (beta) {
         const int32_t r = (int32_t)(e - start) + ra - (second ? S : 0);
-        v.x += beta[r];
-        v.y += beta[r + 1];
+        v.x = __dadd_rn(v.x, beta[r]);
+        v.y = __dadd_rn(v.y, beta[r + 1]);
       }
       __stcs(o2 + (e >> 1), v);
     }

@@ -9,6 +9,20 @@
   .plaid_env$ctx
 }
 
+## options(plaid.gpus = n): the scorers split the columns of X over n devices (one context each; the axis of
+## chunked_crossprod's column loop, R/plaid.R:110-119).  Results are identical for any n.
+.ctxs <- function() {
+  n <- as.integer(getOption("plaid.gpus", 1L))
+  if (is.na(n) || n <= 1L) return(.ctx())
+  have <- length(.plaid_env$ctxs)
+  if (have < n) {
+    if (have == 0L) .plaid_env$ctxs <- list(.ctx())
+    for (d in seq.int(length(.plaid_env$ctxs), n - 1L))
+      .plaid_env$ctxs[[d + 1L]] <- .Call(C_plaidgpu_ctx, as.integer(d))
+  }
+  .plaid_env$ctxs[seq_len(n)]
+}
+
 ## X -> list(kind, p, i, x, dim): dgCMatrix slots are passed as they are (no copy)
 .as_x <- function(X) {
   if (is.null(dim(X))) X <- cbind(X)                                  # R/plaid.R:63
@@ -37,7 +51,7 @@
   rowmap[is.na(rowmap) | duplicated(rn)] <- -1L
   G <- methods::as(matG, "CsparseMatrix")
   if (!inherits(G, "dgCMatrix")) G <- methods::as(methods::as(G, "dMatrix"), "generalMatrix")
-  out <- .Call(C_plaidgpu_score, .ctx(), x$kind, x$p, x$i, x$x, as.integer(x$dim),
+  out <- .Call(C_plaidgpu_score, .ctxs(), x$kind, x$p, x$i, x$x, as.integer(x$dim),
                G@p, G@i, G@x, as.integer(dim(G)), as.integer(rowmap), opts)
   dimnames(out) <- list(colnames(matG), x$dimnames[[2]])
   out
@@ -125,7 +139,7 @@ replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1]) {      # R
 plaid.test <- function(X, y, G, gsetX, tests = c("one", "two", "lm"),
                        metap.method = "fisher", sort.by = "p.meta") {
   if (!all(unique(y) %in% c(0, 1))) stop("elements of y must be 0 or 1")
-  if (is.list(G)) stop("plaid.test: pass the gene sets as a sparse matrix (gmt2mat())")
+  if (is.list(G)) G <- gmt2mat(G)                                      # R/plaid.R: a GMT list is converted first
   gg <- intersect(rownames(G), rownames(X))
   X <- X[gg, , drop = FALSE]
   G <- G[gg, , drop = FALSE]

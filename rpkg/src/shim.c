@@ -58,13 +58,28 @@ static void fill_matrix(plaidgpu_matrix* M, int kind, SEXP p, SEXP i, SEXP x, SE
   M->x = REAL(x);
 }
 
-/* plaid() and the replaid.* scorers */
+/* plaid() and the replaid.* scorers.  `ctx` is one context (external pointer) or a list of contexts on different
+ * devices (options(plaid.gpus = n) in R/plaid.R): the columns are then split over them by plaidgpu_score_multi, one
+ * host thread per device inside the library, the shards landing directly in the result matrix. */
 SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim, SEXP Gp, SEXP Gi, SEXP Gx,
                       SEXP Gdim, SEXP rowmap, SEXP opts) {
-  plaidgpu_ctx* c = get_ctx(ctx);
+  plaidgpu_ctx* cs[16];
+  int nctx = 1;
+  if (TYPEOF(ctx) == VECSXP) {
+    nctx = (int)XLENGTH(ctx);
+    if (nctx < 1 || nctx > 16) Rf_error("plaidgpu: between 1 and 16 contexts expected");
+    for (int k = 0; k < nctx; ++k) cs[k] = get_ctx(VECTOR_ELT(ctx, k));
+  } else {
+    cs[0] = get_ctx(ctx);
+  }
+  plaidgpu_ctx* c = cs[0];
   const int PG = INTEGER(Gdim)[0], S = INTEGER(Gdim)[1];
-  int rc = plaidgpu_set_genesets(c, PG, S, INTEGER(Gp), INTEGER(Gi), REAL(Gx));
-  if (rc != PLAIDGPU_OK) Rf_error("plaidgpu_set_genesets: %s", plaidgpu_last_error(c));
+  /* re-registering the same pattern is a memcmp inside the library: the plan is kept across calls */
+  for (int k = 0; k < nctx; ++k) {
+    int rc0 = plaidgpu_set_genesets(cs[k], PG, S, INTEGER(Gp), INTEGER(Gi), REAL(Gx));
+    if (rc0 != PLAIDGPU_OK) Rf_error("plaidgpu_set_genesets: %s", plaidgpu_last_error(cs[k]));
+  }
+  int rc;
   plaidgpu_matrix M;
   fill_matrix(&M, Rf_asInteger(kind), Xp, Xi, Xx, Xdim);
   plaidgpu_opts o;
@@ -80,12 +95,16 @@ SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim,
   o.tau = opt_dbl(opts, "tau", o.tau);
   o.gsva_ecdf = opt_int(opts, "gsva_ecdf", 0);
   o.nrow_x = (int64_t)opt_dbl(opts, "nrow_x", 0.0);
-  SEXP cs = list_get(opts, "matg_full_colsums");
-  o.matg_full_colsums = cs == R_NilValue ? NULL : REAL(cs);
+  SEXP csums = list_get(opts, "matg_full_colsums");
+  o.matg_full_colsums = csums == R_NilValue ? NULL : REAL(csums);
   o.out_location = PLAIDGPU_HOST;
+  R_CheckUserInterrupt(); /* before the (blocking) device call; the library itself never touches the R API */
   /* S x N may exceed 2^31 elements: Rf_allocMatrix takes ints for the dims, the product is R_xlen_t */
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, S, (int)M.N));
-  rc = plaidgpu_score(c, &M, INTEGER(rowmap), &o, REAL(out));
+  if (nctx > 1 && !(o.scorer == PLAIDGPU_GSVA && o.gsva_ecdf == PLAIDGPU_ROWTF_ECDF))
+    rc = plaidgpu_score_multi(cs, nctx, &M, INTEGER(rowmap), &o, REAL(out));
+  else
+    rc = plaidgpu_score(c, &M, INTEGER(rowmap), &o, REAL(out));
   if (rc != PLAIDGPU_OK) {
     UNPROTECT(1);
     Rf_error("plaidgpu_score: %s", plaidgpu_last_error(c)); /* longjmp: nothing left to release */

@@ -7,6 +7,9 @@ typedef int Rboolean;
 #define TRUE 1
 #define FALSE 0
 #define REALSXP 14
+#define VECSXP 19
+int TYPEOF(SEXP);
+void R_CheckUserInterrupt(void);
 extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 int* INTEGER(SEXP); double* REAL(SEXP); R_xlen_t XLENGTH(SEXP); SEXP VECTOR_ELT(SEXP, R_xlen_t); SEXP STRING_ELT(SEXP, R_xlen_t);
 const char* CHAR(SEXP); SEXP Rf_getAttrib(SEXP, SEXP); int Rf_asInteger(SEXP); double Rf_asReal(SEXP);

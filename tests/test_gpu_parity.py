@@ -112,6 +112,36 @@ def test_multi_tile_many_sets(gpu_ctx):
     assert info["n_tiles"] >= 3 and info["n_tiles"] * info["tile_sets"] >= S
 
 
+def test_tail_pass_tiles_chunks_and_signs(gpu_ctx, monkeypatch):
+    """The tail pass (tail_kernels.cu: rows outside the tensor-core block, gene-major cell tiles of 1,056 columns,
+    integer lo / hi accumulators): several tiles with a ragged last one, one tile per chunk and all tiles in one
+    chunk (bit-identical), stored negative values (borrows through the high word) and a rank scorer whose
+    per-entry terms change sign; all against the oracle."""
+    from plaid_b200 import api
+    P, N, S = 3000, 2300, 2500
+    X = synth.sparse_x_numpy(P, N, seed=41).tocsc()
+    rng = np.random.default_rng(42)
+    X.data = X.data * np.where(rng.random(X.nnz) < 0.3, -1.0, 1.0)  # 30 % negative stored entries
+    G = synth.genesets_numpy(P, S, seed=43, size_cap=(5, 400))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    outs = {}
+    for tiles in ("1", "64"):
+        monkeypatch.setenv("PLAIDGPU_TAIL_TILES", tiles)
+        a = pb.plaid(Xg, Gg, normalize=False, ctx=gpu_ctx).mat
+        b = pb.replaid_sing(Xg, Gg, ctx=gpu_ctx).mat
+        c = pb.plaid(Xg, Gg, ctx=gpu_ctx).mat
+        outs[tiles] = (a, b, c)
+    info = gpu_ctx.plan_info()
+    if not api.EXACT_FP64:
+        assert info["tc_rows"] > 0 and info["tail_rows"] > 0 and N > 2 * info["tail_tile_cells"]
+    for u, v in zip(outs["1"], outs["64"]):
+        assert np.array_equal(u, v)
+    assert rel_err(outs["1"][0], O.plaid(Xo, Go, normalize=False).mat) < tol(TOL)
+    assert rel_err(outs["1"][1], O.replaid_sing(Xo, Go).mat) < tol(TOL)
+    assert rel_err(outs["1"][2], O.plaid(Xo, Go).mat) < tol(TOL)
+
+
 def test_c2_dense_bulk(gpu_ctx):
     P, N, S = 2000, 48, 3000
     X = synth.dense_x_numpy(P, N, seed=synth.SEED0 + 1)
@@ -458,6 +488,34 @@ def test_c_level_multi_context_entry_and_pageable_ring(monkeypatch):
     monkeypatch.setenv("PLAIDGPU_NO_RING", "1")
     c2 = pb.plaid(pb.NamedMatrix(Xb, names), Gn, ctx=ctxs[0]).mat
     assert np.array_equal(a, c2)
+
+
+def test_early_shipping_to_pinned_host_output(monkeypatch):
+    """Pinned host destination: column chunks leave as RAW scores while later chunks are still being scored, and
+    plaidgpu_score_finish fixes them up on the host (api.cu host_fixup_column = k_fixup operation by operation).
+    The result must equal the ordinary path bit for bit: plaid() normalised (host fix-up with medians),
+    replaid.ucell (alpha / beta fix-up), replaid.sing (no normalisation: every chunk is final when it leaves)."""
+    import torch
+    from plaid_b200 import api
+    P, N, S = 1500, 4000, 1800
+    X = synth.sparse_x_numpy(P, N, seed=97)
+    G = synth.genesets_numpy(P, S, seed=98, size_cap=(5, 200))
+    names = synth.gene_names(P)
+    Xn, Gn = pb.NamedMatrix(X, names), pb.NamedMatrix(G, names)
+    ctx = pb.Context(0)
+    monkeypatch.setenv("PLAIDGPU_TAIL_TILES", "1")   # chunks of 1,056 columns
+    calls = [lambda **kw: pb.plaid(Xn, Gn, ctx=ctx, **kw), lambda **kw: pb.replaid_ucell(Xn, Gn, rmax=200, ctx=ctx, **kw),
+             lambda **kw: pb.replaid_sing(Xn, Gn, ctx=ctx, **kw)]
+    for f in calls:
+        monkeypatch.setenv("PLAIDGPU_NO_EARLY", "1")
+        want = f().mat.copy()
+        monkeypatch.delenv("PLAIDGPU_NO_EARLY")
+        monkeypatch.setenv("PLAIDGPU_EARLY_FRAC", "0.6")  # two of the four chunks leave early
+        pinned = torch.empty(S * N, dtype=torch.float64).pin_memory()
+        got = f(out=pinned.numpy().reshape((S, N), order="F")).mat
+        assert np.array_equal(np.asarray(got), want)
+        monkeypatch.delenv("PLAIDGPU_EARLY_FRAC")
+    ctx.close()
 
 
 def test_median_choice_across_shards():

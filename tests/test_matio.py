@@ -138,7 +138,9 @@ def test_mtx_duplicates_crlf_and_errors(tmp_path):
     assert np.array_equal(pb.read_mtx(str(s)).mat.toarray(), np.array([[4, 0, 2], [0, 0, 7], [2, 7, 0]], dtype=float))
     for text, msg in [("hello\n", "banner"), ("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n", "coordinate"),
                       ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n", "truncated"),
-                      ("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n", "out of range")]:
+                      ("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n", "out of range"),
+                      # a non-square "symmetric" file: the mirrored entry (col = row - 1 >= N) used to corrupt the heap
+                      ("%%MatrixMarket matrix coordinate real symmetric\n5 2 2\n5 1 1.0\n4 2 2.0\n", "square")]:
         b = tmp_path / "bad.mtx"
         b.write_text(text)
         with pytest.raises(L.PlaidGpuError, match=msg):

@@ -30,3 +30,14 @@ def test_r_wrappers_keep_reference_signatures():
                 'replaid.gsva <- function(X, matG, tau = 0, rowtf = c("z", "ecdf")[1])']:
         assert sig in src, sig
     assert '[plaid] ERROR. No overlapping features.' in src
+
+
+def test_r_package_exports_the_reference_namespace():
+    """every export of the reference's NAMESPACE (bigomics/plaid NAMESPACE:3-16) is exported and defined here"""
+    ns = open(os.path.join(ROOT, "rpkg", "NAMESPACE")).read()
+    code = open(os.path.join(ROOT, "rpkg", "R", "plaid.R")).read() + open(os.path.join(ROOT, "rpkg", "R", "gmt.R")).read()
+    for name in ["colranks", "gmt2mat", "mat2gmt", "normalize_medians", "plaid", "plaid.test", "read.gmt", "replaid.aucell",
+                 "replaid.gsva", "replaid.scse", "replaid.sing", "replaid.ssgsea", "replaid.ucell", "write.gmt"]:
+        assert f"export({name})" in ns, name
+        assert f"\n{name} <- function(" in "\n" + code, name
+    assert 'getOption("plaid.gpus"' in code and "plaidgpu_score_multi" in open(os.path.join(ROOT, "rpkg", "src", "shim.c")).read()

@@ -64,7 +64,10 @@ if __name__ == "__main__":
         Gn = pb.NamedMatrix(G, names)
         ref = None
         for cfg in os.environ.get("CFGS", "off,1024,2048,3072,4096").split(","):
-            if cfg == "off":
+            if cfg == "auto":
+                os.environ["PLAIDGPU_TC"] = "1"
+                os.environ.pop("PLAIDGPU_TC_K", None)
+            elif cfg == "off":
                 os.environ["PLAIDGPU_TC"] = "0"
             else:
                 os.environ["PLAIDGPU_TC"] = "1"
