@@ -1140,7 +1140,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     const int TC_ = tail_tile_cells();
     int64_t chunk = std::max<int64_t>(ct, ((int64_t)(4ll << 30) / ((int64_t)c->tcK * sl)) / ct * ct);
     if (tail) {
-      int64_t tiles = std::min<int64_t>(8, std::max<int64_t>(1, (int64_t)(4ll << 30) / ((int64_t)c->S * TC_ * 8)));
+      int64_t tiles = std::max<int64_t>(1, (int64_t)(4ll << 30) / ((int64_t)c->S * TC_ * 8));
       if (const char* e = getenv("PLAIDGPU_TAIL_TILES")) tiles = std::max(1, atoi(e));
       chunk = std::max<int64_t>(TC_, std::min<int64_t>(chunk / TC_, tiles) * TC_);
       if (chunk > c->N) chunk = (c->N + TC_ - 1) / TC_ * TC_;
@@ -1164,8 +1164,13 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       CK(c->b_colfb.reserve((size_t)c->N * sizeof(double)));
     }
     tc_flag = c->b_tcflag.as<int>();
-    for (int64_t j0 = 0; j0 < c->N; j0 += chunk) {
-      const int64_t nj = std::min<int64_t>(chunk, c->N - j0);
+    int64_t nj = 0;
+    for (int64_t j0 = 0; j0 < c->N; j0 += nj) {
+      nj = std::min<int64_t>(chunk, c->N - j0);
+      // while chunks leave early for the host (pinned output), keep them small: PCIe starts sooner and the early
+      // part is sized in finer steps; full-size chunks (fewer launches, fuller waves) afterwards
+      if (tail && c->early_out && c->need_norm_hint && j0 < early_limit && !getenv("PLAIDGPU_TAIL_TILES"))
+        nj = std::min<int64_t>(nj, 4 * (int64_t)TC_);
       const int tiles = tail ? (int)((nj + TC_ - 1) / TC_) : 0;
       if (c->dense) {
         CK(launch_tc_prep_dense(p.xx + j0 * (int64_t)c->P, c->P, nj, p.mode, p.a0, p.a1, c->tcK, sl,

@@ -43,7 +43,7 @@ constexpr int TC_KB = 128;           // genes (= bytes of a B row) per K block; 
 constexpr int TC_BST = 5;            // B ring stages (shared memory)
 constexpr int TC_TBOX = 16 * TC_M * 8;  // one tail box: 128 sets x 16 cells of int64 (128-byte swizzled rows)
 constexpr int TC_TBUF = 3 * TC_TBOX;    // tail sums of one accumulator tile (48 cells), double buffered
-constexpr int TC_AST = 4;            // A ring stages (tensor memory, 32 columns each)
+constexpr int TC_AST = 2;            // A ring stages (tensor memory): a stage is a PAIR of K blocks, 64 columns
 constexpr int TC_ACOL = 2 * TC_N;    // first TMEM column of the A ring
 constexpr int TC_BSTAGE = TC_N * TC_KB;  // 24,576 bytes
 #ifndef TC_EXP_GROUPS
@@ -154,13 +154,13 @@ struct TcSmem {
 template <bool RANK, bool CS>
 __device__ __forceinline__ void tc_epi_fast(const uint32_t (&v)[32], uint32_t trow, uint32_t tsw, bool has_tail, int ch,
                                             const TcParams& p, int64_t jc, double inv, double nsv, double* __restrict__ o,
-                                            uint32_t& negbits, bool& anyzero) {
+                                            uint32_t& negbits, bool& anyzero, const int (&edh)[8]) {
   int ed[8];
   double fb[8], cs[8];
   long long tl[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    ed[c] = __ldg(reinterpret_cast<const int*>(p.colinv + jc + c) + 1) - 0x3FF00000;  // (exponent of 2^-e_j) << 20
+    ed[c] = edh[c] - 0x3FF00000;  // (exponent of 2^-e_j) << 20; the high words were fetched one chunk ahead
     if (RANK) fb[c] = __ldg(p.colfb + jc + c);
     if (CS) cs[c] = __ldg(p.colscale + jc + c);
     tl[c] = 0;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
   uint8_t* sB = base;
   uint8_t* sT = base + (size_t)TC_BST * TC_BSTAGE;  // tail boxes (1024-byte aligned: the stage size is a multiple)
   TcSmem* sm = reinterpret_cast<TcSmem*>(sT + 2 * TC_TBUF);
-  const bool has_tail = p.tail != 0 && !(p.dbg & 1);
+  const bool has_tail = p.tail != 0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
   if (tid == TC_W_MMA * 32) {
@@ -272,57 +272,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     // ===== MMA issuer: the whole warp walks the barriers, one elected lane issues (elect.sync keeps the
     // tcgen05 operands in uniform registers; under `if (lane == 0)` ptxas wrapped every tcgen05 instruction in an
     // elect / branch loop and the ~100-instruction issue path, not the tensor pipe, set the pace) =====
+    // One issue block per PAIR of K blocks: the A ring is filled in pairs (one tcgen05.st wait of the expanders per
+    // 256 genes), the barrier polls of the next pair are issued right after the MMAs of the current one so that
+    // their latency runs under the MMAs.
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     const uint64_t bd0 = b_desc(smem_u32(sB));
+    auto adv_b = [&](uint32_t& s_, uint32_t& p_) { if (++s_ == TC_BST) { s_ = 0; p_ ^= 1; } };
+    const int KP = (KBN + 1) >> 1;  // pairs per cell tile (the last one may hold a single K block)
+    const int64_t total_pairs = (int64_t)(ct1 - ct0) * KP;
+    uint32_t sb1 = sb, pb1 = pb;
+    adv_b(sb1, pb1);
+    bool ra = total_pairs > 0 && mbar_try(smem_u32(&sm->a_full[sa]), pa);
+    bool rb0 = total_pairs > 0 && mbar_try(smem_u32(&sm->b_full[sb]), pb);
+    bool rb1 = total_pairs > 0 && KBN > 1 && mbar_try(smem_u32(&sm->b_full[sb1]), pb1);
+    int64_t done = 0;
     for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
       const uint32_t as = t & 1, pacc = (t >> 1) & 1;
       mbar_wait(smem_u32(&sm->acc_empty[as]), pacc ^ 1);
       tc_fence_after();
       const uint32_t dcol = tmem + as * TC_N;
-      for (int kb = 0; kb < KBN; ++kb) {
-        if (!(p.dbg & 2)) mbar_wait(smem_u32(&sm->a_full[sa]), pa);
-        if (!(p.dbg & 4)) mbar_wait(smem_u32(&sm->b_full[sb]), pb);
+      for (int kp = 0; kp < KP; ++kp) {
+        const bool two = 2 * kp + 1 < KBN;
+        if (!ra) mbar_wait(smem_u32(&sm->a_full[sa]), pa);
+        if (!rb0) mbar_wait(smem_u32(&sm->b_full[sb]), pb);
+        if (two && !rb1) mbar_wait(smem_u32(&sm->b_full[sb1]), pb1);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bd = bd0 + (uint64_t)(sb * (TC_BSTAGE >> 4));
-          const uint32_t acol = tmem + TC_ACOL + sa * 32;
+          const uint32_t acol = tmem + TC_ACOL + sa * 64;
+          {
+            const uint64_t bd = bd0 + (uint64_t)(sb * (TC_BSTAGE >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma_i8_ts(dcol, acol + kk * 8, bd + (uint64_t)(kk * 2), TC_IDESC, (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_i8_ts(dcol, acol + kk * 8, bd + (uint64_t)(kk * 2), TC_IDESC, (kp | kk) != 0 ? 1u : 0u);
+            tc_commit(smem_u32(&sm->b_empty[sb]));
+          }
+          if (two) {
+            const uint64_t bd = bd0 + (uint64_t)(sb1 * (TC_BSTAGE >> 4));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) tc_mma_i8_ts(dcol, acol + 32 + kk * 8, bd + (uint64_t)(kk * 2), TC_IDESC, 1u);
+            tc_commit(smem_u32(&sm->b_empty[sb1]));
+          }
           tc_commit(smem_u32(&sm->a_empty[sa]));
-          tc_commit(smem_u32(&sm->b_empty[sb]));
         }
         __syncwarp();
+        ++done;
         if (++sa == TC_AST) { sa = 0; pa ^= 1; }
-        if (++sb == TC_BST) { sb = 0; pb ^= 1; }
+        adv_b(sb, pb);
+        if (two) adv_b(sb, pb);
+        sb1 = sb; pb1 = pb;
+        adv_b(sb1, pb1);
+        const bool more = done < total_pairs;
+        const bool two_next = (kp + 1 < KP) ? (2 * (kp + 1) + 1 < KBN) : (KBN > 1);
+        ra = more && mbar_try(smem_u32(&sm->a_full[sa]), pa);
+        rb0 = more && mbar_try(smem_u32(&sm->b_full[sb]), pb);
+        rb1 = more && two_next && mbar_try(smem_u32(&sm->b_full[sb1]), pb1);
       }
       if (elect_one()) tc_commit(smem_u32(&sm->acc_full[as]));
       __syncwarp();
     }
   } else if (w >= TC_EPI_WARPS && w < TC_W_TMA) {
-    // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, one K block (32 columns) per stage =====
-    // group g (warps 4-7 / 8-11) widens the K blocks q = g, g + 2, ... of this CTA's (cell tile, K block) sequence
-    const int grp = (w - TC_EPI_WARPS) >> 2, wq = (w - TC_EPI_WARPS) & 3;
+    // ===== expanders: bit masks of A -> int8 0/1 in tensor memory, a PAIR of K blocks (2 x 32 columns) per stage:
+    // the tcgen05.st round trip (store, wait::st, fence, arrive) is paid once per 256 genes =====
+    const int wq = (w - TC_EPI_WARPS) & 3;
     const int row = wq * 32 + lane;
     const uint4* __restrict__ ab = p.abits + (size_t)m * KBN * TC_M + row;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const int64_t total = (int64_t)(ct1 - ct0) * KBN;
-    int kb = grp % KBN;
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (grp < total) nxt = __ldg(ab + (size_t)kb * TC_M);
-    for (int64_t q = grp; q < total; q += TC_EXP_GROUPS) {
-      const uint4 bits = nxt;
-      kb += TC_EXP_GROUPS;
-      while (kb >= KBN) kb -= KBN;
-      if (q + TC_EXP_GROUPS < total) nxt = __ldg(ab + (size_t)kb * TC_M);
-      uint32_t v[32];
-      const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
+    const int KP = (KBN + 1) >> 1;
+    const int64_t total = (int64_t)(ct1 - ct0) * KP;
+    auto load_pair = [&](int kp, uint4& b0, uint4& b1) {
+      b0 = __ldg(ab + (size_t)(2 * kp) * TC_M);
+      b1 = (2 * kp + 1 < KBN) ? __ldg(ab + (size_t)(2 * kp + 1) * TC_M) : make_uint4(0, 0, 0, 0);
+    };
+    int kp = 0;
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    if (total > 0) load_pair(0, n0, n1);
+    for (int64_t q = 0; q < total; ++q) {
+      const uint4 bits0 = n0, bits1 = n1;
+      if (++kp == KP) kp = 0;
+      if (q + 1 < total) load_pair(kp, n0, n1);
+      uint32_t v0[32], v1[32];
+      const uint32_t wd0[4] = {bits0.x, bits0.y, bits0.z, bits0.w}, wd1[4] = {bits1.x, bits1.y, bits1.z, bits1.w};
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = (wd[c >> 3] >> (c & 7)) & 0x01010101u;  // bit 8b + k of a word = byte b of column k
+      for (int c = 0; c < 32; ++c) {  // bit 8b + k of a word = byte b of column k
+        v0[c] = (wd0[c >> 3] >> (c & 7)) & 0x01010101u;
+        v1[c] = (wd1[c >> 3] >> (c & 7)) & 0x01010101u;
+      }
       const uint32_t sa = (uint32_t)(q & (TC_AST - 1)), pa = (uint32_t)((q / TC_AST) & 1);
       mbar_wait(smem_u32(&sm->a_empty[sa]), pa ^ 1);
       tc_fence_after();
-      tc_st32(tmem + lane_base + TC_ACOL + sa * 32, v);
+      tc_st32(tmem + lane_base + TC_ACOL + sa * 64, v0);
+      tc_st32(tmem + lane_base + TC_ACOL + sa * 64 + 32, v1);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -350,6 +389,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     const bool fastable = SLICES == 4 && p.final && rows_full && (!rankmode || p.colfb != nullptr) && !(p.dbg & 32);
     constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
     const uint32_t tsw = (uint32_t)(lane & 7);
+    // high words of 2^-e_j for the chunk this warp handles next (fast path): fetched one chunk ahead, so the L2
+    // round trip never sits between the accumulator load and the stores
+    int edn[8];
+    auto fetch_ed = [&](int ct_, int ch_) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int64_t j = (int64_t)ct_ * CT + ch_ * 8 + c;
+        edn[c] = (ct_ < ct1 && j < p.N) ? __ldg(reinterpret_cast<const int*>(p.colinv + j) + 1) : 0x3FF00000;
+      }
+    };
+    if (SLICES == 4 && fastable) fetch_ed(ct0, wh);
     for (int ct = ct0, t = 0; ct < ct1; ++ct, ++t) {
       const uint32_t as = t & 1, pacc = (t >> 1) & 1;
       mbar_wait(smem_u32(&sm->acc_full[as]), pacc);
@@ -364,15 +414,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
       for (int ch = wh; ch < ((p.dbg & 16) ? 0 : TC_N / 32); ch += 2) {
         uint32_t v[32];
         tc_ld32(tmem + lane_base + as * TC_N + ch * 32, v);
+        int edh[8];
+        if (SLICES == 4 && fastable) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) edh[c] = edn[c];
+          if (ch + 2 < TC_N / 32) fetch_ed(ct, ch + 2);
+          else fetch_ed(ct + 1, wh);
+        }
         if (SLICES == 4 && fastable && full) {
           double* o = optr + (int64_t)(ch * 8) * p.ld;
           const int64_t jc8 = j0 + ch * 8;
           if (rankmode) {
-            if (p.colscale) tc_epi_fast<true, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
-            else tc_epi_fast<true, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+            if (p.colscale) tc_epi_fast<true, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero, edh);
+            else tc_epi_fast<true, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero, edh);
           } else {
-            if (p.colscale) tc_epi_fast<false, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
-            else tc_epi_fast<false, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero);
+            if (p.colscale) tc_epi_fast<false, true>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero, edh);
+            else tc_epi_fast<false, false>(v, trow, tsw, has_tail, ch, p, jc8, inv, nsv, o, negbits, anyzero, edh);
           }
           continue;
         }

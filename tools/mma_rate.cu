@@ -66,6 +66,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 struct Sm {
   unsigned long long bar;
+  unsigned long long dummy[8];
   uint32_t tmem_base;
   volatile int stop;
 };
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(320, 1) k_rate(int N, int mode, int batches, i
   for (int i = tid; i < (256 + 128) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01010101u;
   if (tid == 0) {
     mbar_init(smem_u32(&sm->bar), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&sm->dummy[i]), 1);
     sm->stop = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -101,6 +103,55 @@ __global__ void __launch_bounds__(320, 1) k_rate(int N, int mode, int batches, i
     long long t0 = clock64();
     uint32_t ph = 0;
     for (int b = 0; b < batches; ++b) {
+      if (mode & 16) {
+        // the issue loop of k_tc_score: per K block two barrier polls (always complete here: parity 1 of a fresh
+        // barrier), fence, one elected lane issues 4 MMAs + 2 commits
+        for (int i0 = 0; i0 < per_batch; i0 += 4) {
+          mbar_wait(smem_u32(&sm->dummy[4]), 1);
+          mbar_wait(smem_u32(&sm->dummy[5]), 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_ts(tmem, acol + ((i0 + kk) & 15) * 8, bd + (uint64_t)(kk * 2), idesc, 1u);
+            tc_commit(smem_u32(&sm->dummy[(i0 >> 2) & 1]));
+            tc_commit(smem_u32(&sm->dummy[2 + ((i0 >> 2) & 1)]));
+          }
+          __syncwarp();
+        }
+      } else if (mode & 32) {
+        // the same with the polls of the NEXT pair issued after the MMAs and two K blocks per elected block
+        bool r0 = mbar_try(smem_u32(&sm->dummy[4]), 1), r1 = mbar_try(smem_u32(&sm->dummy[5]), 1);
+        bool r2 = mbar_try(smem_u32(&sm->dummy[6]), 1), r3 = mbar_try(smem_u32(&sm->dummy[7]), 1);
+        for (int i0 = 0; i0 < per_batch; i0 += 8) {
+          if (!r0) mbar_wait(smem_u32(&sm->dummy[4]), 1);
+          if (!r1) mbar_wait(smem_u32(&sm->dummy[5]), 1);
+          if (!r2) mbar_wait(smem_u32(&sm->dummy[6]), 1);
+          if (!r3) mbar_wait(smem_u32(&sm->dummy[7]), 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) mma_ts(tmem, acol + ((i0 + kk) & 15) * 8, bd + (uint64_t)((kk & 3) * 2), idesc, 1u);
+            tc_commit(smem_u32(&sm->dummy[0]));
+            tc_commit(smem_u32(&sm->dummy[1]));
+            tc_commit(smem_u32(&sm->dummy[2]));
+            tc_commit(smem_u32(&sm->dummy[3]));
+          }
+          __syncwarp();
+          r0 = mbar_try(smem_u32(&sm->dummy[4]), 1); r1 = mbar_try(smem_u32(&sm->dummy[5]), 1);
+          r2 = mbar_try(smem_u32(&sm->dummy[6]), 1); r3 = mbar_try(smem_u32(&sm->dummy[7]), 1);
+        }
+      } else if (mode & 64) {
+        // 4 MMAs + 2 commits per elected block, no polls
+        for (int i0 = 0; i0 < per_batch; i0 += 4) {
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) mma_ts(tmem, acol + ((i0 + kk) & 15) * 8, bd + (uint64_t)(kk * 2), idesc, 1u);
+            tc_commit(smem_u32(&sm->dummy[(i0 >> 2) & 1]));
+            tc_commit(smem_u32(&sm->dummy[2 + ((i0 >> 2) & 1)]));
+          }
+          __syncwarp();
+        }
+      } else {
       for (int i0 = 0; i0 < per_batch; i0 += 4) {
         if (elect_one()) {
 #pragma unroll
@@ -112,6 +163,7 @@ __global__ void __launch_bounds__(320, 1) k_rate(int N, int mode, int batches, i
           }
         }
         __syncwarp();
+      }
       }
       if (elect_one()) tc_commit(smem_u32(&sm->bar));
       __syncwarp();
