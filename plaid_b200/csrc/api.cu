@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -149,7 +150,30 @@ struct plaidgpu_ctx {
   double* early_out = nullptr;
   int64_t early_cols = 0;
   cudaEvent_t ev_early = nullptr, ev_d2h[2] = {};
+  // the early copies are enqueued by a helper thread: cudaMemcpyAsync blocks its caller once a few GB are queued on
+  // the copy engine, and the thread that launches the scoring kernels must never wait for PCIe
+  static constexpr int SHIP_EV = 64;
+  cudaEvent_t ev_ship[SHIP_EV] = {};
+  std::thread shipper;
+  std::mutex ship_m;
+  std::condition_variable ship_cv;
+  std::vector<std::pair<int64_t, int64_t>> ship_q;  // (first column, columns) of the chunks to ship, in order
+  bool ship_done = true;
   double d2h_ms_per_col = 0.0, comp_ms_per_col = 0.0;  // measured by the previous call: sizes the early part
+  double t_begin = 0.0, t_known = 0.0;  // wall clock: call started / scores and medians known
+  // host CSC input of plaid(): i / x cross PCIe in pieces on their own stream; a column chunk waits only for the
+  // piece that holds its last entry, so scoring (and the first D2H) starts after ~1/50 of the upload
+  static constexpr int H2D_EV = 64;
+  cudaStream_t h2d_stream = nullptr;
+  cudaEvent_t ev_h2d[H2D_EV] = {};
+  int h2d_pieces = 0;
+  int64_t h2d_piece = 0;
+  bool h2d_pending = false;
+  const int32_t* xp_host = nullptr;
+  // mailbox: pinned, device-mapped host memory the GPU writes small results into (launch_copy_words)
+  void* mbox = nullptr;
+  void* mbox_dev = nullptr;
+  size_t mbox_cap = 0;
   std::string err;
   int64_t launches = 0;
   double ms[4] = {0, 0, 0, 0};  // 0 score, 1 colstats, 2 fixup, 3 rank
@@ -206,6 +230,21 @@ struct plaidgpu_ctx {
 };
 
 namespace {
+
+// PLAIDGPU_TRACE=1: wall-clock marks of the host path on stderr (development)
+double trace_now() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+void trace(const char* what) {
+  static const bool on = getenv("PLAIDGPU_TRACE") != nullptr;
+  static double t0 = 0.0;
+  if (!on) return;
+  const double t = trace_now();
+  if (strcmp(what, "begin") == 0) t0 = t;
+  fprintf(stderr, "[plaidgpu trace] %8.2f ms  %s\n", t - t0, what);
+}
 
 int fail(plaidgpu_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
@@ -538,7 +577,7 @@ int device_minmax(plaidgpu_ctx* c, const double* d, int64_t n, double* mn, doubl
   return PLAIDGPU_OK;
 }
 
-int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X) {
+int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X, bool piecewise = false) {
   c->dense = (X->kind == PLAIDGPU_DENSE);
   c->P = X->P;
   c->N = X->N;
@@ -562,13 +601,47 @@ int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X) {
     c->nnz = last;
     int rc = to_device<int32_t>(c, X->p, (size_t)X->N + 1, X->location, c->b_xp, &c->xp);
     if (rc) return rc;
-    rc = to_device<int32_t>(c, X->i, (size_t)c->nnz, X->location, c->b_xi, &c->xi);
-    if (rc) return rc;
-    rc = to_device<double>(c, X->x, (size_t)c->nnz, X->location, c->b_xx, &c->xx);
-    if (rc) return rc;
+    c->h2d_pending = false;
+    c->xp_host = nullptr;
+    int64_t piece_min = (int64_t)4 << 20;  // entries per piece (48 MB); test knob: PLAIDGPU_H2D_PIECE
+    if (const char* e = getenv("PLAIDGPU_H2D_PIECE")) piece_min = std::max<int64_t>(1024, atoll(e));
+    if (piecewise && X->location == PLAIDGPU_HOST && c->nnz > 2 * piece_min && !getenv("PLAIDGPU_NO_H2D_PIPE")) {
+      // pieces of i and x on the upload stream, one event each (see plaidgpu_ctx::ev_h2d)
+      CK(c->b_xi.reserve((size_t)c->nnz * sizeof(int32_t)));
+      CK(c->b_xx.reserve((size_t)c->nnz * sizeof(double)));
+      c->h2d_piece = std::max<int64_t>(piece_min, (c->nnz + plaidgpu_ctx::H2D_EV - 1) / plaidgpu_ctx::H2D_EV);
+      c->h2d_pieces = (int)((c->nnz + c->h2d_piece - 1) / c->h2d_piece);
+      CK(cudaEventRecord(c->ev_chunk[1], c->stream));  // buffers may still be read by the previous call's kernels
+      CK(cudaStreamWaitEvent(c->h2d_stream, c->ev_chunk[1], 0));
+      for (int k = 0; k < c->h2d_pieces; ++k) {
+        const int64_t e0 = (int64_t)k * c->h2d_piece, n = std::min<int64_t>(c->h2d_piece, c->nnz - e0);
+        CK(cudaMemcpyAsync(c->b_xi.as<int32_t>() + e0, X->i + e0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->h2d_stream));
+        CK(cudaMemcpyAsync(c->b_xx.as<double>() + e0, X->x + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->h2d_stream));
+        CK(cudaEventRecord(c->ev_h2d[k], c->h2d_stream));
+      }
+      c->xi = c->b_xi.as<int32_t>();
+      c->xx = c->b_xx.as<double>();
+      c->h2d_pending = true;
+      c->xp_host = X->p;
+    } else {
+      rc = to_device<int32_t>(c, X->i, (size_t)c->nnz, X->location, c->b_xi, &c->xi);
+      if (rc) return rc;
+      rc = to_device<double>(c, X->x, (size_t)c->nnz, X->location, c->b_xx, &c->xx);
+      if (rc) return rc;
+    }
   } else {
     return fail(c, PLAIDGPU_ERR_ARG, "unknown matrix kind");
   }
+  return PLAIDGPU_OK;
+}
+
+// the compute stream waits for the upload pieces up to entry `upto` (exclusive); upto < 0: all of X
+int h2d_wait(plaidgpu_ctx* c, int64_t upto) {
+  if (!c->h2d_pending) return PLAIDGPU_OK;
+  int k = c->h2d_pieces - 1;
+  if (upto >= 0 && upto < c->nnz) k = (int)(std::max<int64_t>(upto - 1, 0) / c->h2d_piece);
+  CK(cudaStreamWaitEvent(c->stream, c->ev_h2d[k], 0));
+  if (k == c->h2d_pieces - 1) c->h2d_pending = false;
   return PLAIDGPU_OK;
 }
 
@@ -630,19 +703,100 @@ int run_colstats(plaidgpu_ctx* c, int which) {
   return PLAIDGPU_OK;
 }
 
+// ---- helper thread that enqueues the early result blocks (see plaidgpu_ctx::shipper) ----
+void ship_join(plaidgpu_ctx* c) {
+  if (!c->shipper.joinable()) return;
+  {
+    std::lock_guard<std::mutex> lk(c->ship_m);
+    c->ship_done = true;
+  }
+  c->ship_cv.notify_all();
+  c->shipper.join();
+}
+void ship_body(plaidgpu_ctx* c) {
+  cudaSetDevice(c->device);
+  size_t next = 0;
+  for (;;) {
+    std::pair<int64_t, int64_t> job;
+    {
+      std::unique_lock<std::mutex> lk(c->ship_m);
+      c->ship_cv.wait(lk, [&] { return next < c->ship_q.size() || c->ship_done; });
+      if (next >= c->ship_q.size()) return;
+      job = c->ship_q[next];
+    }
+    cudaStreamWaitEvent(c->copy_stream, c->ev_ship[next], 0);
+    cudaMemcpyAsync(c->early_out + job.first * (int64_t)c->S, c->raw + job.first * (int64_t)c->S,
+                    (size_t)job.second * c->S * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream);
+    cudaEventRecord(c->ev_early, c->copy_stream);
+    ++next;
+  }
+}
+// called by the scoring thread right after the kernels of a chunk were launched
+int ship_chunk(plaidgpu_ctx* c, int64_t j0, int64_t nj) {
+  size_t k;
+  {
+    std::lock_guard<std::mutex> lk(c->ship_m);
+    k = c->ship_q.size();
+  }
+  if (k >= (size_t)plaidgpu_ctx::SHIP_EV) return 1;  // out of events: the rest leaves after the fix-up
+  CK(cudaEventRecord(c->ev_ship[k], c->stream));
+  {
+    std::lock_guard<std::mutex> lk(c->ship_m);
+    c->ship_q.emplace_back(j0, nj);
+  }
+  if (!c->shipper.joinable()) {
+    c->ship_done = false;
+    c->shipper = std::thread(ship_body, c);
+  }
+  c->ship_cv.notify_all();
+  return PLAIDGPU_OK;
+}
+
+// Small device -> host reads (8-byte words) through the mailbox: a kernel stores into mapped host memory, so the
+// read does not wait behind result blocks queued in the copy engine.  items: {host dst, device src, words}
+struct SmallRead {
+  void* host;
+  const void* dev;
+  int64_t words;
+};
+int read_small(plaidgpu_ctx* c, const SmallRead* it, int n) {
+  int64_t total = 0;
+  for (int k = 0; k < n; ++k) total += it[k].words;
+  if (total <= 0) {
+    CK(cudaStreamSynchronize(c->stream));
+    return PLAIDGPU_OK;
+  }
+  if (c->mbox_cap < (size_t)total * 8) {
+    if (c->mbox) cudaFreeHost(c->mbox);
+    c->mbox = nullptr;
+    c->mbox_cap = 0;
+    const size_t want = std::max<size_t>((size_t)total * 8, (size_t)1 << 20);
+    CK(cudaHostAlloc(&c->mbox, want, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&c->mbox_dev, c->mbox, 0));
+    c->mbox_cap = want;
+  }
+  int64_t off = 0;
+  for (int k = 0; k < n; ++k) {
+    CK(launch_copy_words(it[k].dev, static_cast<char*>(c->mbox_dev) + off * 8, it[k].words, c->stream));
+    off += it[k].words;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  off = 0;
+  for (int k = 0; k < n; ++k) {
+    if (it[k].words > 0) memcpy(it[k].host, static_cast<char*>(c->mbox) + off * 8, (size_t)it[k].words * 8);
+    off += it[k].words;
+  }
+  return PLAIDGPU_OK;
+}
+
 int fetch_medians(plaidgpu_ctx* c) {
   c->h_med_all.resize((size_t)c->N);
   c->h_med_nz.resize((size_t)c->N);
   c->h_colmin.resize((size_t)c->N);
-  if (c->N) {
-    if (c->have_all)
-      CK(cudaMemcpyAsync(c->h_med_all.data(), c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (c->have_nz)
-      CK(cudaMemcpyAsync(c->h_med_nz.data(), c->b_med_nz.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_colmin.data(), c->b_colmin.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  }
-  CK(cudaStreamSynchronize(c->stream));
-  return PLAIDGPU_OK;
+  const SmallRead it[3] = {{c->h_med_all.data(), c->b_med_all.p, c->have_all ? c->N : 0},
+                           {c->h_med_nz.data(), c->b_med_nz.p, c->have_nz ? c->N : 0},
+                           {c->h_colmin.data(), c->b_colmin.p, c->N}};
+  return read_small(c, it, 3);
 }
 
 // make the plain (want_nz = false) or the non-zero median of every column available on device and host
@@ -737,13 +891,16 @@ int plaidgpu_init(int device, plaidgpu_ctx** out) try {
   if (!c) return PLAIDGPU_ERR_NOMEM;
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return PLAIDGPU_ERR_CUDA;
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   for (auto& ev : c->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming);
+  for (auto& ev : c->ev_ship) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (auto& ev : c->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto& ev : c->ev_d2h) cudaEventCreate(&ev);
   *out = c;
   return PLAIDGPU_OK;
@@ -765,7 +922,12 @@ void plaidgpu_destroy(plaidgpu_ctx* c) {
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_chunk) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_ring) if (ev) cudaEventDestroy(ev);
+  ship_join(c);
   if (c->ev_early) cudaEventDestroy(c->ev_early);
+  for (auto& ev : c->ev_ship) if (ev) cudaEventDestroy(ev);
+  if (c->mbox) cudaFreeHost(c->mbox);
+  for (auto& ev : c->ev_h2d) if (ev) cudaEventDestroy(ev);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   for (auto& ev : c->ev_d2h) if (ev) cudaEventDestroy(ev);
   for (auto& r : c->ring) if (r) cudaFreeHost(r);
   delete c->pool;
@@ -863,6 +1025,7 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !rowmap || !opts || !local) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->have_g) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_set_genesets has not been called");
+  trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;
   c->computed = false;
@@ -872,9 +1035,14 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   // gsva scores a dense z-matrix whatever the storage of X
   int rc = build_plan(c, X->P, rowmap, opts->tile_sets, X->kind == PLAIDGPU_DENSE || opts->scorer == PLAIDGPU_GSVA);
   if (rc) return rc;
-  rc = load_matrix(c, X);
+  rc = load_matrix(c, X, opts->scorer == PLAIDGPU_PLAID);  // plaid(): the upload runs under the scoring of earlier chunks
   if (rc) return rc;
 
+  if (opts->scorer != PLAIDGPU_PLAID) {  // ranks / column sums / row moments read all of X in this call
+    rc = h2d_wait(c, -1);
+    if (rc) return rc;
+  }
+  c->t_begin = trace_now();
   memset(local, 0, sizeof(*local));
   local->x_min = INFINITY;
   local->x_max = -INFINITY;
@@ -985,6 +1153,7 @@ int plaidgpu_score_begin(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     local->rank_max = mx;
     c->score_vals = c->b_rank.as<double>();
   }
+  trace("begin done (X uploaded / ranked)");
   c->in_call = true;
   return PLAIDGPU_OK;
 } catch (const std::bad_alloc&) {
@@ -1090,6 +1259,8 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   }
   p.out = c->raw;
   // early shipping: with a pinned host destination, finished column chunks start crossing PCIe at once
+  ship_join(c);
+  c->ship_q.clear();
   c->early_out = nullptr;
   c->early_cols = 0;
   int64_t early_limit = 0;
@@ -1099,7 +1270,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     if (c->need_norm_hint) {
       // normalised scores need mean(medians) of ALL columns: only as many chunks go out raw as PCIe can move
       // while the rest is scored (rates of the previous call; a conservative guess for the first one)
-      frac = (c->d2h_ms_per_col > 0.0 && c->comp_ms_per_col > 0.0) ? 1.1 * c->comp_ms_per_col / c->d2h_ms_per_col : 0.12;
+      frac = (c->d2h_ms_per_col > 0.0 && c->comp_ms_per_col > 0.0) ? 1.1 * c->comp_ms_per_col / c->d2h_ms_per_col : 0.15;
       if (const char* e = getenv("PLAIDGPU_EARLY_FRAC")) frac = atof(e);
       frac = std::min(0.6, std::max(0.0, frac));
     }
@@ -1116,7 +1287,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   unsigned long long* smin = nullptr;
   if (c->need_norm) {  // the score kernels report their smallest final score (see ensure_median)
     CK(c->b_smin.reserve(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->b_smin.p, 0xFF, sizeof(unsigned long long), c->stream));
+    CK(launch_fill_u32(c->b_smin.p, 0xFFFFFFFFu, 2, c->stream));
     smin = c->b_smin.as<unsigned long long>();
   }
   p.smin = smin;
@@ -1125,14 +1296,18 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   const bool use_tc = c->tcK > 0 && !o.exact_fp64 && c->N > 0;
   const int* tc_flag = nullptr;
   bool compacted = false;
+  if (!(use_tc && !c->dense)) {  // only the chunk loop below waits piece by piece
+    int rcw = h2d_wait(c, -1);
+    if (rcw) return rcw;
+  }
   if (use_tc) {
     // tensor cores: fixed-point digit rows of the block (k_tc_prep_*), then t(G) bits x digits (k_tc_score).
     // A non-finite block entry cannot be quantised: it raises a device flag, the tensor-core kernel returns at
     // once and the fp64 gather passes below (otherwise no-ops) redo the block.
     const int sl = c->tc_slices;
     const int ct = tc_cells_per_tile(sl);
-    CK(c->b_tcflag.reserve(sizeof(int)));
-    CK(cudaMemsetAsync(c->b_tcflag.p, 0, sizeof(int), c->stream));
+    CK(c->b_tcflag.reserve(8));
+    CK(launch_fill_u32(c->b_tcflag.p, 0u, 2, c->stream));
     CK(c->b_colinv.reserve((size_t)c->N * sizeof(double)));
     // column chunks keep the digit-row operand within ~4 GiB whatever N is; with a tail pass a chunk is a whole
     // number of tail tiles and its int64 tail sums (S x chunk) stay within ~4 GB too
@@ -1172,11 +1347,15 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       if (tail && c->early_out && c->need_norm_hint && j0 < early_limit && !getenv("PLAIDGPU_TAIL_TILES"))
         nj = std::min<int64_t>(nj, 4 * (int64_t)TC_);
       const int tiles = tail ? (int)((nj + TC_ - 1) / TC_) : 0;
+      if (c->h2d_pending) {  // this chunk's entries (and everything before them) must have landed
+        int rcw = h2d_wait(c, c->xp_host ? (int64_t)c->xp_host[j0 + nj] : -1);
+        if (rcw) return rcw;
+      }
       if (c->dense) {
         CK(launch_tc_prep_dense(p.xx + j0 * (int64_t)c->P, c->P, nj, p.mode, p.a0, p.a1, c->tcK, sl,
                                 c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0, c->b_tcflag.as<int>(), c->stream));
       } else {
-        if (tail) CK(cudaMemsetAsync(c->b_tcnt.p, 0, (size_t)tiles * c->Pt * sizeof(uint32_t), c->stream));
+        if (tail) CK(launch_fill_u32(c->b_tcnt.p, 0u, (int64_t)tiles * c->Pt, c->stream));
         CK(launch_tc_prep_csc(c->xp + j0, c->xi, p.xx, p.r0 ? p.r0 + j0 : nullptr, c->d_dmap.as<uint16_t>(), nj, p.mode,
                               p.a0, p.a1, c->tcK, sl, c->b_tcB.as<signed char>(), c->b_colinv.as<double>() + j0,
                               c->b_ci.as<int32_t>(), c->b_cx.as<double>(), c->b_ce.as<int32_t>() + j0,
@@ -1218,15 +1397,22 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       CK(launch_tc_score(t, c->b_tcB.as<signed char>(), c->tcK, sl, c->stream));
       c->launches += 2;
       if (c->early_out && t.final && j0 + nj <= early_limit) {
-        CK(cudaEventRecord(c->ev_chunk[0], c->stream));
-        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[0], 0));
-        CK(cudaMemcpyAsync(c->early_out + j0 * (int64_t)c->S, c->raw + j0 * (int64_t)c->S, (size_t)nj * c->S * sizeof(double),
-                           cudaMemcpyDeviceToHost, c->copy_stream));
-        CK(cudaEventRecord(c->ev_early, c->copy_stream));
-        c->early_cols = j0 + nj;
+        const int rcs = ship_chunk(c, j0, nj);
+        if (rcs == PLAIDGPU_OK) c->early_cols = j0 + nj;
+        else if (rcs < 0) return rcs;
+        else early_limit = 0;
       }
     }
+    {  // no more early blocks: the helper drains its list and exits (joined in plaidgpu_score_finish)
+      std::lock_guard<std::mutex> lk(c->ship_m);
+      c->ship_done = true;
+    }
+    c->ship_cv.notify_all();
     compacted = !c->dense && c->nnz > 0;
+    {
+      int rcw = h2d_wait(c, -1);
+      if (rcw) return rcw;
+    }
   }
   if (c->gblocks > 0) {
     GatherParams g{};
@@ -1282,6 +1468,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     c->launches += 1;
   }
   CK(cudaEventRecord(c->ev[1], c->stream));
+  trace("compute: score kernels enqueued");
 
   scal->score_min = INFINITY;
   c->have_all = c->have_nz = false;
@@ -1292,8 +1479,11 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     // coincide; < 0 -> the global minimum is negative too, the plain median is used; == 0 -> the non-zero
     // median, unless another shard holds a negative score (then the plain one is computed on demand).
     unsigned long long key = ~0ull;
-    CK(cudaMemcpyAsync(&key, c->b_smin.p, sizeof(key), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    {
+      const SmallRead it[1] = {{&key, c->b_smin.p, 1}};
+      int rcs = read_small(c, it, 1);
+      if (rcs) return rcs;
+    }
     c->local_min = (key == ~0ull) ? INFINITY : host_value_of(key);
     int which = COLSTATS_BOTH;
     if (!c->want_both && !colstats_small(c->S)) {
@@ -1305,7 +1495,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[3], c->stream));
     if (which == COLSTATS_ALL && c->local_min > 0.0 && c->N) {  // no zeros: the two medians are the same numbers
-      CK(cudaMemcpyAsync(c->b_med_nz.p, c->b_med_all.p, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      CK(launch_copy_words(c->b_med_all.p, c->b_med_nz.p, c->N, c->stream));  // by a kernel: copy engines may be busy with result blocks
       c->have_nz = true;
     }
     rc = fetch_medians(c);
@@ -1314,9 +1504,14 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
   CK(cudaStreamSynchronize(c->stream));
   if (c->early_cols > 0) {
     // a non-finite entry sent the call through the fp64 passes AFTER chunks had left: ship everything again
-    int flag = 0;
-    CK(cudaMemcpy(&flag, c->b_tcflag.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) {
+    unsigned long long flag = 0;  // b_tcflag is reserved with 8 bytes: the int flag sits in the low half
+    {
+      const SmallRead it[1] = {{&flag, c->b_tcflag.p, 1}};
+      int rcs = read_small(c, it, 1);
+      if (rcs) return rcs;
+    }
+    if ((int)(flag & 0xFFFFFFFFull)) {
+      ship_join(c);
       CK(cudaStreamSynchronize(c->copy_stream));
       c->early_cols = 0;
     }
@@ -1331,6 +1526,8 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
     for (int64_t j = 0; j < c->N; ++j) mn = fmin(mn, c->h_colmin[j]);
     scal->score_min = mn;
   }
+  c->t_known = trace_now();
+  trace("compute done (scores + medians)");
   c->computed = true;
   return PLAIDGPU_OK;
 } catch (const std::bad_alloc&) {
@@ -1479,6 +1676,7 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
     // columns [0, E) already left as RAW scores while the rest was being scored (plaidgpu_score_compute): a helper
     // thread fixes them up in the caller's matrix — the arithmetic of k_fixup, operation by operation — while the
     // remaining blocks are fixed up on the device and follow over PCIe
+    ship_join(c);  // every early block is enqueued on the copy stream from here on
     const int64_t E = (c->early_out == out) ? std::min<int64_t>(c->early_cols, N) : 0;
     c->early_out = nullptr;
     c->early_cols = 0;
@@ -1509,6 +1707,7 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
       patcher = std::thread([=] {
         cudaSetDevice(dev);
         cudaEventSynchronize(evE);
+        trace("patcher: early D2H landed");
         pool->run([=](int part, int parts) {
           const int64_t lo = E * part / parts, hi = E * (part + 1) / parts;
           for (int64_t j = lo; j < hi; ++j) host_fixup_column(out + j * (int64_t)S, S, hm ? hm[j] : 0.0, hm != nullptr, cc, alpha, hb);
@@ -1532,17 +1731,20 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
                          cudaMemcpyDeviceToHost, c->copy_stream));
     }
     if (!first) CK(cudaEventRecord(c->ev_d2h[1], c->copy_stream));
+    trace("finish: late blocks enqueued");
     CK(cudaEventRecord(c->ev[5], c->stream));
     cudaError_t e1 = cudaStreamSynchronize(c->stream);
     cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);
+    trace("finish: D2H done");
     if (patcher.joinable()) patcher.join();
+    trace("finish: host fix-up of the early part done");
     CK(e1);
     CK(e2);
     if (!first && N - E >= 64) {  // rates for the next call's early part
       float dms = 0.f;
       if (cudaEventElapsedTime(&dms, c->ev_d2h[0], c->ev_d2h[1]) == cudaSuccess && dms > 0.f) {
         c->d2h_ms_per_col = (double)dms / (double)(N - E);
-        c->comp_ms_per_col = (c->ms[0] + c->ms[1]) / (double)N;
+        c->comp_ms_per_col = (c->ms[0] + c->ms[1]) / (double)N;  // kernel time: the wall clock of compute also counts the early copies it overlaps
       }
     }
   }
@@ -1941,6 +2143,7 @@ int plaidgpu_crossprod(plaidgpu_ctx* c, const plaidgpu_matrix* Y, const int32_t*
 int plaidgpu_row_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const double* mean, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;
   c->computed = false;
@@ -1959,6 +2162,7 @@ int plaidgpu_row_ecdf(plaidgpu_ctx* c, double* x, int64_t N, int32_t rows, int l
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!x && N > 0 && rows > 0) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (N < 0 || rows < 0 || N > 0x7fffffff) return fail(c, PLAIDGPU_ERR_ARG, "bad dimensions for row ecdf");
+  trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;
   c->computed = false;
@@ -1993,6 +2197,7 @@ int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int i
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (ties < PLAIDGPU_TIES_AVERAGE || ties > PLAIDGPU_TIES_MAX) return fail(c, PLAIDGPU_ERR_ARG, "unsupported ties.method");
+  trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;
   c->computed = false;
@@ -2088,6 +2293,7 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* c, const double* x, int32_t S, int6
                                int location, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (S <= 0 || N < 0 || (N > 0 && (!x || !out))) return fail(c, PLAIDGPU_ERR_ARG, "bad argument");
+  trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;
   c->computed = false;

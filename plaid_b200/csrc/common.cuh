@@ -152,6 +152,7 @@ cudaError_t launch_tc_score(const TcParams& p, const signed char* Bd, int Kp, in
 
 // tail_kernels.cu — rows of a sparse X outside the tensor-core block: gene-major cell tiles, one warp per (tile, set)
 int tail_tile_cells();
+cudaError_t launch_fill_u32(void* p, uint32_t v, int64_t n32, cudaStream_t st);  // n32 32-bit words := v, by a kernel
 cudaError_t launch_tile_scan(uint32_t* cnt, int32_t Pt, int tiles, uint32_t* rowptr, uint32_t* total, cudaStream_t st);
 cudaError_t launch_tile_place(const int32_t* xp, const int32_t* xe, const int32_t* oi, const double* ox, const double* r0,
                               const int32_t* tmap, const double* colinv, int64_t N, int mode, double a0, double a1,
@@ -182,6 +183,8 @@ cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, in
 // out = 4 * S doubles {sum0, sumsq0, sum1, sumsq1}; fixed summation order
 cudaError_t launch_group_moments(const double* x, int64_t ld, int32_t S, int64_t N, const int32_t* y, int nchunk,
                                  double* partial, double* out, cudaStream_t st);
+// nwords 8-byte words device -> host-mapped (cudaHostAllocMapped) memory by a kernel, bypassing the copy engine
+cudaError_t launch_copy_words(const void* src, void* dst_mapped, int64_t nwords, cudaStream_t st);
 // global min / max of a device array of n doubles, NaN ignored (na.rm = TRUE); res[0]=min res[1]=max
 cudaError_t launch_minmax(const double* x, int64_t n, double* res2, cudaStream_t st);
 

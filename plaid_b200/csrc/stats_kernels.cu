@@ -791,6 +791,13 @@ __global__ void __launch_bounds__(256) k_group_combine(const double* __restrict_
   out[i] = a;
 }
 
+// device -> host-mapped memory by SM stores: small control values (minimum key, flags, medians) must not queue
+// behind gigabytes of result blocks in the copy engine
+__global__ void __launch_bounds__(256) k_copy_words(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst,
+                                                    int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 __global__ void k_minmax_init(unsigned long long* res) {
   res[0] = ~0ull;
   res[1] = 0ull;
@@ -830,7 +837,7 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
   }
   // single-pass kernel, then the exact three-pass kernel on whatever it rejected
   // d_fail (1 int) and d_list (N int64) are caller-owned scratch: no allocation on the hot path
-  cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
+  cudaError_t e = launch_fill_u32(d_fail, 0u, 1, st);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
   const size_t smem = which == COLSTATS_BOTH ? sizeof(Stats2Smem) : STATS2_SMEM_ONE;
@@ -894,6 +901,14 @@ cudaError_t launch_group_moments(const double* x, int64_t ld, int32_t S, int64_t
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_group_combine<<<(unsigned)((4 * (int64_t)S + 255) / 256), 256, 0, st>>>(partial, S, nchunk, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy_words(const void* src, void* dst_mapped, int64_t nwords, cudaStream_t st) {
+  if (nwords <= 0) return cudaSuccess;
+  int64_t grid = (nwords + 255) / 256;
+  if (grid > 148 * 4) grid = 148 * 4;
+  k_copy_words<<<(unsigned)grid, 256, 0, st>>>(static_cast<const unsigned long long*>(src), static_cast<unsigned long long*>(dst_mapped), nwords);
   return cudaGetLastError();
 }
 

@@ -103,6 +103,12 @@ __global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ 
   }
 }
 
+// fills by kernel, not cudaMemsetAsync: a memset may be scheduled on a copy engine and then waits behind the
+// gigabyte result blocks that are leaving for the host on another stream
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ p, uint32_t v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 struct TailParams {
   const uint32_t* tptr;    // [S + 1] set -> its tail members
   const uint16_t* tidx;    // tail ids, ascending inside a set
@@ -219,6 +225,14 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p)
 
 }  // namespace
 
+cudaError_t launch_fill_u32(void* p, uint32_t v, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  int64_t grid = (n + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_fill_u32<<<(unsigned)grid, 256, 0, st>>>(static_cast<uint32_t*>(p), v, n);
+  return cudaGetLastError();
+}
+
 int tail_tile_cells() { return 1056; }  // 22 tensor-core cell tiles of 48
 
 size_t tail_smem_bytes() { return (size_t)TAIL_WARPS * tail_tile_cells() * 6; }
@@ -263,7 +277,7 @@ cudaError_t launch_tail(const uint32_t* tptr, const uint16_t* tidx, const int32_
   const size_t smem = tail_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+  e = launch_fill_u32(counter, 0u, 1, st);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

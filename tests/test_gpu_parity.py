@@ -504,6 +504,7 @@ def test_early_shipping_to_pinned_host_output(monkeypatch):
     Xn, Gn = pb.NamedMatrix(X, names), pb.NamedMatrix(G, names)
     ctx = pb.Context(0)
     monkeypatch.setenv("PLAIDGPU_TAIL_TILES", "1")   # chunks of 1,056 columns
+    monkeypatch.setenv("PLAIDGPU_H2D_PIECE", "20000")  # plaid(): X crosses PCIe in ~20 pieces, chunks wait for theirs only
     calls = [lambda **kw: pb.plaid(Xn, Gn, ctx=ctx, **kw), lambda **kw: pb.replaid_ucell(Xn, Gn, rmax=200, ctx=ctx, **kw),
              lambda **kw: pb.replaid_sing(Xn, Gn, ctx=ctx, **kw)]
     for f in calls:
