@@ -8,6 +8,9 @@
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <condition_variable>
@@ -43,6 +46,39 @@ struct DevBuf {
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// Large host copies into a destination that will not be read again soon (the caller's result matrix): streaming
+// (non-temporal) stores skip the read-for-ownership of every destination line, which otherwise doubles the write
+// traffic; glibc's memcpy only switches to them far above the 5 MB a copy thread handles at a time.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void copy_stream_avx2(char* d, const char* s, size_t n) {
+  while (n && ((uintptr_t)d & 31)) {
+    *d++ = *s++;
+    --n;
+  }
+  size_t v = n / 128;
+  for (; v; --v) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)s), b = _mm256_loadu_si256((const __m256i*)(s + 32));
+    const __m256i c2 = _mm256_loadu_si256((const __m256i*)(s + 64)), e = _mm256_loadu_si256((const __m256i*)(s + 96));
+    _mm256_stream_si256((__m256i*)d, a);
+    _mm256_stream_si256((__m256i*)(d + 32), b);
+    _mm256_stream_si256((__m256i*)(d + 64), c2);
+    _mm256_stream_si256((__m256i*)(d + 96), e);
+    s += 128;
+    d += 128;
+  }
+  _mm_sfence();
+  n &= 127;
+  if (n) memcpy(d, s, n);
+}
+static void copy_streaming(void* d, const void* s, size_t n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("PLAIDGPU_NO_NT_COPY");
+  if (avx2 && n >= 4096) copy_stream_avx2(static_cast<char*>(d), static_cast<const char*>(s), n);
+  else memcpy(d, s, n);
+}
+#else
+static void copy_streaming(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+#endif
 
 // Blocking memcpy split over a few persistent host threads: moves finished column blocks from the pinned ring
 // into a PAGEABLE caller buffer (what an R caller hands in: Rf_allocMatrix memory) at memory speed, while the
@@ -107,7 +143,7 @@ class CopyPool {
       const std::function<void(int, int)>* fn = fn_;
       lk.unlock();
       if (fn) (*fn)(i, (int)parts);
-      else if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+      else if (hi > lo) copy_streaming(d + lo, s + lo, hi - lo);
       lk.lock();
       if (--pending_ == 0) cv_done_.notify_all();
     }
@@ -577,6 +613,46 @@ int device_minmax(plaidgpu_ctx* c, const double* d, int64_t n, double* mn, doubl
   return PLAIDGPU_OK;
 }
 
+// pinned ring + copy threads shared by the pageable upload (load_matrix) and the pageable result path (finish)
+int ensure_ring(plaidgpu_ctx* c) {
+  const size_t want = (size_t)256 << 20;
+  if (!c->ring[0] || c->ring_bytes < want) {
+    for (int i = 0; i < plaidgpu_ctx::RING; ++i) {
+      if (c->ring[i]) cudaFreeHost(c->ring[i]);
+      c->ring[i] = nullptr;
+      CK(cudaMallocHost(&c->ring[i], want));
+      if (!c->ev_ring[i]) CK(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+    }
+    c->ring_bytes = want;
+  }
+  if (!c->pool) {
+    int nt = (int)std::min<unsigned>(12, std::max(2u, std::thread::hardware_concurrency() * 3 / 4));
+    if (const char* e = getenv("PLAIDGPU_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+    c->pool = new CopyPool(nt);
+  }
+  return PLAIDGPU_OK;
+}
+
+// pageable host array -> device through the pinned ring: the copy threads fill slot k + 1 while slot k crosses PCIe
+// (the driver's own staging of a pageable cudaMemcpyAsync is single-threaded: ~11 GB/s measured)
+int upload_pageable(plaidgpu_ctx* c, void* dev, const void* host, size_t bytes, cudaStream_t st) {
+  int rc = ensure_ring(c);
+  if (rc) return rc;
+  const char* src = static_cast<const char*>(host);
+  char* dst = static_cast<char*>(dev);
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += c->ring_bytes, ++k) {
+    const size_t n = std::min(c->ring_bytes, bytes - off);
+    const int slot = k % plaidgpu_ctx::RING;
+    if (k >= plaidgpu_ctx::RING) CK(cudaEventSynchronize(c->ev_ring[slot]));
+    c->pool->copy(c->ring[slot], src + off, n);
+    CK(cudaMemcpyAsync(dst + off, c->ring[slot], n, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ev_ring[slot], st));
+  }
+  for (int i = 0; i < std::min(k, (int)plaidgpu_ctx::RING); ++i) CK(cudaEventSynchronize(c->ev_ring[i]));  // slots are free again
+  return PLAIDGPU_OK;
+}
+
 int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X, bool piecewise = false) {
   c->dense = (X->kind == PLAIDGPU_DENSE);
   c->P = X->P;
@@ -605,7 +681,20 @@ int load_matrix(plaidgpu_ctx* c, const plaidgpu_matrix* X, bool piecewise = fals
     c->xp_host = nullptr;
     int64_t piece_min = (int64_t)4 << 20;  // entries per piece (48 MB); test knob: PLAIDGPU_H2D_PIECE
     if (const char* e = getenv("PLAIDGPU_H2D_PIECE")) piece_min = std::max<int64_t>(1024, atoll(e));
-    if (piecewise && X->location == PLAIDGPU_HOST && c->nnz > 2 * piece_min && !getenv("PLAIDGPU_NO_H2D_PIPE")) {
+    const bool big_pageable = X->location == PLAIDGPU_HOST && c->nnz > ((int64_t)4 << 20) && is_pageable(X->x) &&
+                              !getenv("PLAIDGPU_NO_RING");
+    if (big_pageable) {
+      // a pageable X (an R dgCMatrix): staged through the pinned ring by the copy threads
+      CK(c->b_xi.reserve((size_t)c->nnz * sizeof(int32_t)));
+      CK(c->b_xx.reserve((size_t)c->nnz * sizeof(double)));
+      CK(cudaStreamSynchronize(c->stream));  // the buffers may still be read by the previous call's kernels
+      rc = upload_pageable(c, c->b_xi.p, X->i, (size_t)c->nnz * sizeof(int32_t), c->stream);
+      if (rc) return rc;
+      rc = upload_pageable(c, c->b_xx.p, X->x, (size_t)c->nnz * sizeof(double), c->stream);
+      if (rc) return rc;
+      c->xi = c->b_xi.as<int32_t>();
+      c->xx = c->b_xx.as<double>();
+    } else if (piecewise && X->location == PLAIDGPU_HOST && c->nnz > 2 * piece_min && !getenv("PLAIDGPU_NO_H2D_PIPE")) {
       // pieces of i and x on the upload stream, one event each (see plaidgpu_ctx::ev_h2d)
       CK(c->b_xi.reserve((size_t)c->nnz * sizeof(int32_t)));
       CK(c->b_xx.reserve((size_t)c->nnz * sizeof(double)));
@@ -1629,20 +1718,9 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
       // A pageable destination (an R matrix) would make every cudaMemcpyAsync a staged, synchronous copy at a
       // fraction of the PCIe rate.  Blocks go through a pinned ring instead and the copy threads move block
       // k - 1 into the caller's matrix while block k crosses PCIe and block k + 1 is fixed up.
-      const size_t want = (size_t)64 << 20;
-      if (!c->ring[0] || c->ring_bytes < want) {
-        for (int i = 0; i < plaidgpu_ctx::RING; ++i) {
-          if (c->ring[i]) cudaFreeHost(c->ring[i]);
-          c->ring[i] = nullptr;
-          CK(cudaMallocHost(&c->ring[i], want));
-          if (!c->ev_ring[i]) CK(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
-        }
-        c->ring_bytes = want;
-      }
-      if (!c->pool) {
-        int nt = (int)std::min<unsigned>(12, std::max(2u, std::thread::hardware_concurrency() * 3 / 4));
-        if (const char* e = getenv("PLAIDGPU_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
-        c->pool = new CopyPool(nt);
+      {
+        int rcr = ensure_ring(c);
+        if (rcr) return rcr;
       }
       const int64_t chunk = std::max<int64_t>(1, (int64_t)(c->ring_bytes / ((size_t)S * 8)));
       const int64_t nchunks = (N + chunk - 1) / chunk;
