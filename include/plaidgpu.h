@@ -261,6 +261,14 @@ int plaidgpu_normalize_medians(plaidgpu_ctx* ctx, const double* x, int32_t S, in
 int plaidgpu_group_moments(plaidgpu_ctx* ctx, const double* x, int32_t S, int64_t N, const int32_t* y,
                            int location, double* out);
 
+/* The same reductions FUSED onto the scoring call (row f1 as SURVEY.md states it): scores X like plaidgpu_score
+ * (HOST or DEVICE X), then reduces the (median-normalised) scores per set and sample group in one pass over the raw
+ * scores still on the device — the normalisation is applied in registers, the S x N matrix is neither written in
+ * its final form nor copied to the host; 4 * S doubles come back (layout as above).  Equal, bit for bit, to
+ * plaidgpu_score followed by plaidgpu_group_moments.  Replaces R/plaid.R:423-431 (plaid() + Rfast::ttests). */
+int plaidgpu_score_group_moments(plaidgpu_ctx* ctx, const plaidgpu_matrix* X, const int32_t* rowmap,
+                                 const plaidgpu_opts* opts, const int32_t* y, double* out);
+
 /* ---- gene-set ingestion ("next" row f2): host-side, no GPU needed -------------------------- */
 
 /* read.gmt() + gmt2mat() with default arguments (reference R/gmt-utils.R:99-125, 19-66): a GMT text

@@ -450,6 +450,38 @@ def group_moments(gsetX, y, *, ctx=None):
     return out
 
 
+def score_group_moments(X: NamedMatrix, matG: NamedMatrix, y, *, ctx=None, **opts_kw):
+    """plaid() (or another scorer through `opts_kw`) fused with the group reductions of plaid.test(tests="lm")
+    (`plaidgpu_score_group_moments`, R/plaid.R:423-431): the S x N score matrix stays on the device as raw scores,
+    the normalisation is applied in registers while reducing, 4 x S doubles come back.  Returns (4, S) like
+    group_moments, or None on no overlap."""
+    ctx = ctx or default_context()
+    if X.rownames is None or matG.rownames is None:
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    rowmap = make_rowmap(X.rownames, matG.rownames)
+    if not (rowmap >= 0).any():
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    ctx.set_genesets(matG.mat)
+    keep: list = []
+    M = _matrix_struct(X.mat, keep)
+    y32 = np.ascontiguousarray(np.asarray(y), dtype=np.int32)
+    if y32.size != M.N:
+        raise ValueError("length(y) must equal ncol(X)")
+    kw = dict(scorer=L.PLAID, stats_mean=1, normalize=1)
+    kw.update(opts_kw)
+    o = _opts(ctx.lib, **kw)
+    out = np.empty((4, int(matG.mat.shape[1])), dtype=np.float64)
+    rc = ctx.lib.plaidgpu_score_group_moments(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(o), y32.ctypes.data,
+                                              out.ctypes.data)
+    if rc == L.ERR_NOOVERLAP:
+        _message("[plaid] ERROR. No overlapping features.")
+        return None
+    ctx.check(rc)
+    return out
+
+
 def plaid_test(X: NamedMatrix, y, G: NamedMatrix, gsetX: Optional[NamedMatrix] = None, tests=("one", "two", "lm"),
                metap_method: str = "fisher", sort_by: str = "p.meta", *, ctx=None):
     """`plaid.test(X, y, G, gsetX, tests=c("one","two","lm"), metap.method="fisher", sort.by="p.meta")`
@@ -502,10 +534,11 @@ def plaid_test(X: NamedMatrix, y, G: NamedMatrix, gsetX: Optional[NamedMatrix] =
             f = mean1 - mean0
             P["two"], Fs["two"] = 2.0 * stats.t.sf(np.abs(f / np.sqrt(varsum)), np.maximum(dof, 1)), f
         if "lm" in tests:  # R/plaid.R:423-433
-            if gsetX is None:
+            if gsetX is None:  # scores never leave the device: reductions fused onto the scoring call
                 _message("[plaid.test] computing plaid scores...")
-                gsetX = plaid(NamedMatrix(Xs, gg, X.colnames), NamedMatrix(Gs, gg, G.colnames), ctx=ctx)
-            gm = group_moments(gsetX.mat, y, ctx=ctx)
+                gm = score_group_moments(NamedMatrix(Xs, gg, X.colnames), NamedMatrix(Gs, gg, G.colnames), y, ctx=ctx)
+            else:
+                gm = group_moments(gsetX.mat, y, ctx=ctx)
             m1, m2 = gm[0] / n0, gm[2] / n1  # ina 1 = (y == 0), ina 2 = (y == 1)
             v1 = (gm[1] - n0 * m1 ** 2) / (n0 - 1)
             v2 = (gm[3] - n1 * m2 ** 2) / (n1 - 1)

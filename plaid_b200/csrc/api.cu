@@ -206,6 +206,9 @@ struct plaidgpu_ctx {
   int64_t h2d_piece = 0;
   bool h2d_pending = false;
   const int32_t* xp_host = nullptr;
+  // plaidgpu_score_group_moments: finish reduces the (fixed-up on the fly) scores instead of shipping them
+  const int32_t* mom_y = nullptr;
+  double* mom_out = nullptr;
   // mailbox: pinned, device-mapped host memory the GPU writes small results into (launch_copy_words)
   void* mbox = nullptr;
   void* mbox_dev = nullptr;
@@ -1671,7 +1674,7 @@ int plaidgpu_combine_medians(int ignore_zero_opt, double score_min, const double
 
 int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
-  if (!scal || (!out && c->N > 0)) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  if (!scal || (!out && c->N > 0 && !c->mom_y)) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
   if (!c->computed) return fail(c, PLAIDGPU_ERR_STATE, "plaidgpu_score_compute has not been called");
   CK(cudaSetDevice(c->device));
   const plaidgpu_opts& o = c->opts;
@@ -1701,6 +1704,31 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
     fix = true;
   }
 
+  if (c->mom_y) {
+    // score -> test: per-set sums / sums of squares of the normalised scores by sample group, the fix-up applied in
+    // registers; the S x N matrix stays on the device as raw scores and nothing but 4 S doubles goes back
+    const int32_t* y = c->mom_y;
+    double* mo = c->mom_out;
+    c->mom_y = nullptr;
+    c->mom_out = nullptr;
+    const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
+    CK(c->b_i32.reserve((size_t)std::max<int64_t>(N, 1) * sizeof(int32_t)));
+    if (N) CK(cudaMemcpyAsync(c->b_i32.p, y, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(c->b_rowa.reserve((size_t)nchunk * 4 * S * sizeof(double)));
+    CK(c->b_rowb.reserve((size_t)4 * S * sizeof(double)));
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(launch_group_moments(c->raw, S, S, N, c->b_i32.as<int32_t>(), nchunk, c->b_rowa.as<double>(), c->b_rowb.as<double>(),
+                            c->stream, fix, med, cc, alpha, beta));
+    c->launches += 2;
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    const SmallRead it[1] = {{mo, c->b_rowb.p, 4 * (int64_t)S}};
+    int rcm = read_small(c, it, 1);
+    if (rcm) return rcm;
+    float msm = 0.f;
+    cudaEventElapsedTime(&msm, c->ev[4], c->ev[5]);
+    c->ms[2] = msm;
+    return PLAIDGPU_OK;
+  }
   c->raw_valid = false;  // the fix-up below rewrites the raw scores in place
   CK(cudaEventRecord(c->ev[4], c->stream));
   if (o.out_location == PLAIDGPU_DEVICE) {
@@ -2025,6 +2053,40 @@ int plaidgpu_score(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* row
     if (rc) return fail(c, rc, "combine_medians failed");
   }
   return plaidgpu_score_finish(c, &s, out);
+} catch (const std::bad_alloc&) {
+  return PLAIDGPU_ERR_NOMEM;
+} catch (...) {
+  return PLAIDGPU_ERR_ARG;
+}
+
+// score -> test fused ("next" row f1 as specified): plaid() / a replaid.* scorer followed by the per-set group moments of
+// plaid.test(tests = "lm") (R/plaid.R:426-431) without the S x N matrix ever leaving the device or being written in
+// its normalised form.  Bit-identical to plaidgpu_score + plaidgpu_group_moments.
+int plaidgpu_score_group_moments(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
+                                 const int32_t* y, double* out) try {
+  if (!c) return PLAIDGPU_ERR_ARG;
+  if (!X || !opts || !y || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
+  plaidgpu_opts o = *opts;
+  o.out_location = PLAIDGPU_HOST;  // raw scores in the library's device buffer
+  plaidgpu_scalars s;
+  int rc = plaidgpu_score_begin(c, X, rowmap, &o, &s);
+  if (rc) return rc;
+  rc = plaidgpu_score_compute(c, &s, nullptr);
+  if (rc) return rc;
+  if (c->need_norm) {
+    const bool iz = o.ignore_zero < 0 ? (s.score_min == 0.0) : (o.ignore_zero != 0);
+    rc = ensure_median(c, iz);
+    if (rc) return rc;
+    const double* m = iz ? c->h_med_nz.data() : c->h_med_all.data();
+    rc = plaidgpu_combine_medians(o.ignore_zero, s.score_min, m, m, c->N, &s);
+    if (rc) return fail(c, rc, "combine_medians failed");
+  }
+  c->mom_y = y;
+  c->mom_out = out;
+  rc = plaidgpu_score_finish(c, &s, nullptr);
+  c->mom_y = nullptr;
+  c->mom_out = nullptr;
+  return rc;
 } catch (const std::bad_alloc&) {
   return PLAIDGPU_ERR_NOMEM;
 } catch (...) {

@@ -757,16 +757,27 @@ __global__ void __launch_bounds__(256) k_minmax(const double* __restrict__ x, in
 
 // row sums / sums of squares of a column-major S x N matrix by column group y[j] in {0,1}.
 // grid = (row blocks, column chunks); partial[chunk][4][S] are combined in chunk order by k_group_combine.
+// FIX: the values are RAW scores and the fix-up of normalize_medians / replaid.ucell (k_fixup: alpha * (x + (c - med_j))
+// [+ beta_s], the same operations in the same order) is applied in registers — the normalised matrix is never
+// written (plaidgpu_score_group_moments: score -> test without materialising S x N for the host).
+template <bool FIX>
 __global__ void __launch_bounds__(256) k_group_partial(const double* __restrict__ x, int64_t ld, int32_t S, int64_t N,
                                                        const int32_t* __restrict__ y, int nchunk,
-                                                       double* __restrict__ partial) {
+                                                       double* __restrict__ partial, const double* __restrict__ med,
+                                                       double c, double alpha, const double* __restrict__ beta) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int ch = blockIdx.y;
   const int64_t j0 = (N * ch) / nchunk, j1 = (N * (ch + 1)) / nchunk;
   double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   if (r < S) {
+    const double b = (FIX && beta) ? beta[r] : 0.0;
     for (int64_t j = j0; j < j1; ++j) {
-      const double v = __ldcs(x + j * ld + r);
+      double v = __ldcs(x + j * ld + r);
+      if (FIX) {
+        const double shift = (med ? -med[j] : 0.0) + c;
+        v = __dmul_rn(alpha, __dadd_rn(v, shift));
+        if (beta) v = __dadd_rn(v, b);
+      }
       if (y[j]) {
         s1 += v;
         q1 += v * v;
@@ -894,10 +905,12 @@ cudaError_t launch_fixup(const double* x, double* out, int64_t ld, int32_t S, in
 }
 
 cudaError_t launch_group_moments(const double* x, int64_t ld, int32_t S, int64_t N, const int32_t* y, int nchunk,
-                                 double* partial, double* out, cudaStream_t st) {
+                                 double* partial, double* out, cudaStream_t st, bool fix, const double* med, double c,
+                                 double alpha, const double* beta) {
   if (S <= 0) return cudaSuccess;
   dim3 g((unsigned)((S + 255) / 256), (unsigned)nchunk);
-  k_group_partial<<<g, 256, 0, st>>>(x, ld, S, N, y, nchunk, partial);
+  if (fix) k_group_partial<true><<<g, 256, 0, st>>>(x, ld, S, N, y, nchunk, partial, med, c, alpha, beta);
+  else k_group_partial<false><<<g, 256, 0, st>>>(x, ld, S, N, y, nchunk, partial, nullptr, 0.0, 1.0, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_group_combine<<<(unsigned)((4 * (int64_t)S + 255) / 256), 256, 0, st>>>(partial, S, nchunk, out);

@@ -372,6 +372,7 @@ def test_chunked_crossprod_matches(gpu_ctx):
 
 def test_plaid_test_statistics(gpu_ctx):
     """plaid.test (R/plaid.R:392-474): GPU reductions + host distribution functions vs the oracle restatement"""
+    from plaid_b200 import _lib as L
     P, N, S = 900, 60, 120
     X = synth.sparse_x_numpy(P, N, seed=111, density=0.3)
     G = synth.genesets_numpy(P, S, seed=112, size_cap=(5, 120))
@@ -387,6 +388,18 @@ def test_plaid_test_statistics(gpu_ctx):
     assert np.all(np.diff(got[0][:, got[1].index("p.meta")]) >= 0)
     gm = pb.group_moments(np.arange(12.0).reshape(3, 4), [0, 1, 1, 0], ctx=gpu_ctx)
     assert np.array_equal(gm, [[3, 11, 19], [9, 65, 185], [3, 11, 19], [5, 61, 181]])
+    # f1 as specified: the reductions fused onto the scoring call (scores stay on the device, normalisation applied
+    # in registers) are the reductions of the materialised normalised matrix, bit for bit — plaid and a rank scorer
+    Xn, Gn = pb.NamedMatrix(X, names), pb.NamedMatrix(G, names, sets)
+    for kw, full in ((dict(), pb.plaid(Xn, Gn, ctx=gpu_ctx)),
+                     (dict(normalize=0), pb.plaid(Xn, Gn, normalize=False, ctx=gpu_ctx)),
+                     (dict(scorer=L.UCELL, rmax=200.0), pb.replaid_ucell(Xn, Gn, rmax=200, ctx=gpu_ctx))):
+        fused = pb.score_group_moments(Xn, Gn, y, ctx=gpu_ctx, **kw)
+        assert np.array_equal(fused, pb.group_moments(full.mat, y, ctx=gpu_ctx))
+    o_full = O.plaid(O.Named(X, names), O.Named(G, names)).mat
+    fused = pb.score_group_moments(Xn, Gn, y, ctx=gpu_ctx)
+    want_gm = np.stack([o_full[:, y == 0].sum(1), (o_full[:, y == 0] ** 2).sum(1), o_full[:, y == 1].sum(1), (o_full[:, y == 1] ** 2).sum(1)])
+    assert rel_err(fused, want_gm) < tol(1e-10)
 
 
 def test_degenerate_shapes(gpu_ctx):
