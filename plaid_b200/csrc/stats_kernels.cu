@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace plaidgpu {
 
@@ -658,6 +659,348 @@ __global__ void __launch_bounds__(NT) k_colstats_fast(const double* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-median variant of the one-pass kernel (the launch normalize_medians needs once the median flavour is
+// known — every scoring call).  The bracket lives entirely in FP32: rn(.) is monotone, so f(v1) < f(v2) implies
+// v1 < v2 and the three classes {f < lo}, {lo <= f <= hi}, {f > hi} are ordered by exact value — the full pass
+// needs no fp64 test at all: one F2F, two FSETP, a predicated count and (for ~8 % of the rows) a predicated
+// store of the raw bits into the thread's PRIVATE candidate slots (slot k of thread t = cand[k * NT + t]: no
+// ballots, no atomics, conflict-free).  The bracket ends need not be sample values either: a two-digit radix
+// select over the 1024 float keys of the sample (22 of 32 bits) replaces the bitonic sort; the ends are the bin
+// edges around the wanted sample ranks.  The wanted ranks are then selected exactly among the candidates
+// (doubles) by a radix select that starts at the first bit in which the bracket ends differ.  Rejects (rank
+// outside the bracket, slot overflow, any NaN in the column) go to the three-pass kernel as before.
+constexpr int TCAP = 20;   // private candidate slots per thread (expected ~7-10; moved out beyond 16)
+constexpr int OVF = 256;   // shared overflow slots (threads whose private slots are full: ~2 % of the threads)
+
+struct Stats3Smem {
+  // sampling phase scratch lives in cand (not yet in use): samp[SAMP] | h1[NBIN] | h2a[NBIN] | h2b[NBIN] (28 KB)
+  unsigned long long cand[TCAP * NT + OVF];
+  unsigned hist[NBIN];
+  unsigned part[NT];
+  BinHit hit;
+  float lof, hif;
+  unsigned mcount, novf, below, nzero, ncand, nsmall, cle;
+  int bad;
+  unsigned long long minkey, nxt, resA;
+  unsigned long long small[64];
+};
+
+__device__ __forceinline__ unsigned fkey_of(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fvalue_of(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <bool NZ>
+__global__ void __launch_bounds__(NT) k_colstats_one(const double* __restrict__ x, int64_t ld, int32_t S, int64_t N,
+                                                     double* __restrict__ med, double* __restrict__ colmin,
+                                                     int* __restrict__ fail_count, int64_t* __restrict__ fail_list) {
+  extern __shared__ unsigned char smem_raw3[];
+  Stats3Smem& s = *reinterpret_cast<Stats3Smem*>(smem_raw3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned* const samp = reinterpret_cast<unsigned*>(s.cand);
+  unsigned* const h1 = samp + SAMP;
+  unsigned* const h2a = h1 + NBIN;
+  unsigned* const h2b = h2a + NBIN;
+
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+    const double* __restrict__ c = x + j * ld;
+    // ---- sample: float keys, invalid (NaN, or zero when the zeros are dropped) = ~0 ----
+    for (int i = tid; i < 3 * NBIN; i += NT) h1[i] = 0;
+    if (tid == 0) {
+      s.mcount = s.novf = s.below = s.nzero = s.ncand = 0;
+      s.bad = 0;
+      s.minkey = ~0ull;
+    }
+    __syncthreads();
+    {
+      unsigned mv = 0;
+      for (int i = tid; i < SAMP; i += NT) {
+        const int pos = (int)(((int64_t)i * S) / SAMP);
+        const double v = c[pos];
+        const bool valid = (v == v) && !(NZ && v == 0.0);
+        const unsigned k = valid ? fkey_of(__double2float_rn(v)) : ~0u;
+        samp[i] = k;
+        if (valid) {
+          atomicAdd(&h1[k >> 21], 1u);
+          ++mv;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mv += __shfl_xor_sync(FULL, mv, o);
+      if (lane == 0 && mv) atomicAdd(&s.mcount, mv);
+    }
+    __syncthreads();
+    const unsigned mcount = s.mcount;
+    int ra = -1, rb = -1;  // wanted sample ranks; -1 = open end
+    if (mcount >= 48) {
+      const double mid = 0.5 * (double)(mcount - 1);
+      const double delta = 1.25 * sqrt((double)mcount) + 2.0;  // 2.5 sigma of a binomial(m, 1/2) rank
+      const int a = (int)floor(mid - delta), b = (int)ceil(mid + delta);
+      if (a >= 0) ra = a;
+      if (b <= (int)mcount - 1) rb = b;
+    }
+    // second digit of the two ends (block-uniform control flow: ra / rb / mcount are uniform)
+    BinHit ha{0, 0, 0}, hb{0, 0, 0};
+    if (ra >= 0) ha = find_bin(h1, NBIN, (unsigned)ra, s.part, &s.hit);
+    __syncthreads();
+    if (rb >= 0) hb = find_bin(h1, NBIN, (unsigned)rb, s.part, &s.hit);
+    __syncthreads();
+    if (ra >= 0 || rb >= 0) {
+      for (int i = tid; i < SAMP; i += NT) {
+        const unsigned k = samp[i];
+        if (k == ~0u) continue;
+        const unsigned top = k >> 21, d2 = (k >> 10) & 2047u;
+        if (ra >= 0 && top == (unsigned)ha.bin) atomicAdd(&h2a[d2], 1u);
+        if (rb >= 0 && top == (unsigned)hb.bin) atomicAdd(&h2b[d2], 1u);
+      }
+    }
+    __syncthreads();
+    BinHit ga{0, 0, 0}, gb{0, 0, 0};
+    if (ra >= 0) ga = find_bin(h2a, NBIN, (unsigned)ra - ha.before, s.part, &s.hit);
+    __syncthreads();
+    if (rb >= 0) gb = find_bin(h2b, NBIN, (unsigned)rb - hb.before, s.part, &s.hit);
+    __syncthreads();
+    if (tid == 0) {
+      // bin edges as floats: low edge of the bin holding sample rank a, high edge of the one holding rank b
+      float lof = -INFINITY, hif = INFINITY;
+      if (ra >= 0) {
+        const unsigned klo = ((unsigned)ha.bin << 21) | ((unsigned)ga.bin << 10);
+        const float f = fvalue_of(klo);
+        if (f == f) lof = f;
+      }
+      if (rb >= 0) {
+        const unsigned khi = ((unsigned)hb.bin << 21) | ((unsigned)gb.bin << 10) | 1023u;
+        const float f = fvalue_of(khi);
+        if (f == f) hif = f;
+      }
+      s.lof = lof;
+      s.hif = hif;
+    }
+    __syncthreads();
+    const float lof = s.lof, hif = s.hif;
+    __syncthreads();  // the sampling scratch (inside cand) is dead from here on
+
+    // ---- the one full pass ----
+    unsigned bel = 0, nz = 0, cnt = 0, flushed = 0;
+    double minv = INFINITY;
+    unsigned long long* const mine = s.cand + tid;
+    // a thread whose private slots are nearly full (~2 % of the threads) moves them to the shared overflow area;
+    // checked once per 4 rows so the per-row path has no capacity test
+    auto flush = [&]() {
+      const unsigned base = atomicAdd(&s.novf, cnt);
+      for (unsigned k = 0; k < cnt; ++k)
+        if (base + k < (unsigned)OVF) s.cand[TCAP * NT + base + k] = mine[k * NT];
+      flushed += cnt;
+      cnt = 0;
+    };
+    // zeros (dropped when NZ) have f = +-0: they are "below" iff lo > 0 and inside the bracket iff lo <= 0 <= hi —
+    // both uniform per column, so the per-row path only counts them
+    const bool zin = NZ && lof <= 0.f && hif >= 0.f;
+    auto visit = [&](double v, bool ZIN) {
+      const float f = __double2float_rn(v);
+      minv = v < minv ? v : minv;             // NaN never selected
+      const bool lt = f < lof;
+      bool cd = !(lt || f > hif);             // NaN: neither -> candidate, rejects the column after the pass
+      if (NZ) {
+        const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+        const bool isz = ((hi + hi) | lo) == 0u;
+        nz += isz;
+        if (ZIN) cd = cd && !isz;
+      }
+      bel += lt;
+      if (cd) mine[cnt * NT] = (unsigned long long)__double_as_longlong(v);
+      cnt += cd;
+    };
+    constexpr int UNR = 8;  // loads of 8 rows are issued before any of them is consumed
+    int l0 = 0;
+    for (; l0 + NT * UNR <= S; l0 += NT * UNR) {
+      double vv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) vv[u] = __ldcs(c + l0 + u * NT + tid);
+#pragma unroll
+      for (int h = 0; h < UNR; h += 4) {
+        if (cnt > (unsigned)(TCAP - 4)) flush();
+        if (zin) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) visit(vv[h + u], true);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) visit(vv[h + u], false);
+        }
+      }
+    }
+    for (int l = l0 + tid; l < S; l += NT) {
+      if (cnt >= (unsigned)TCAP) flush();
+      visit(__ldcs(c + l), zin);
+    }
+    if (NZ && lof > 0.f) bel -= nz;  // the zeros were counted as below
+
+    // ---- block totals ----
+    {
+      unsigned tot = cnt + flushed;
+      unsigned long long mink = minv == INFINITY ? ~0ull : key_of(minv);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        bel += __shfl_xor_sync(FULL, bel, o);
+        nz += __shfl_xor_sync(FULL, nz, o);
+        tot += __shfl_xor_sync(FULL, tot, o);
+        const unsigned long long mk = __shfl_xor_sync(FULL, mink, o);
+        mink = mk < mink ? mk : mink;
+      }
+      if (lane == 0) {
+        atomicAdd(&s.below, bel);
+        if (NZ) atomicAdd(&s.nzero, nz);
+        atomicAdd(&s.ncand, tot);
+        atomicMin(&s.minkey, mink);
+      }
+    }
+    // raw bits -> order-preserving keys in place; any NaN rejects the column
+    const unsigned own = cnt < (unsigned)TCAP ? cnt : (unsigned)TCAP;
+    {
+      bool nan_seen = false;
+      for (unsigned k = 0; k < own; ++k) {
+        const double v = __longlong_as_double((long long)mine[k * NT]);
+        nan_seen |= (v != v);
+        mine[k * NT] = key_of(v);
+      }
+      __syncthreads();  // novf final
+      const unsigned novf = s.novf < (unsigned)OVF ? s.novf : (unsigned)OVF;
+      for (unsigned i = tid; i < novf; i += NT) {
+        const double v = __longlong_as_double((long long)s.cand[TCAP * NT + i]);
+        nan_seen |= (v != v);
+        s.cand[TCAP * NT + i] = key_of(v);
+      }
+      if (nan_seen) s.bad = 1;
+    }
+    __syncthreads();
+    const unsigned novf = s.novf;
+    const unsigned count = (unsigned)S - (NZ ? s.nzero : 0u);  // valid values the median runs over (no NaN if !bad)
+    const unsigned ka = count ? (count - 1) / 2 : 0, kb = count / 2;
+    const unsigned below = s.below, ncand = s.ncand;
+    bool good = !s.bad && novf <= (unsigned)OVF;
+    if (count > 0 && (ka < below || kb >= below + ncand)) good = false;
+    unsigned long long A = 0, B = 0;
+    if (good && count > 0) {  // block-uniform
+      // ---- exact selection of rank qa among the candidates (and its successor if the count is even) ----
+      const unsigned qa = ka - below, qb = kb - below;
+      // every candidate lies in [lo - 1 ulp(float), hi + 1 ulp(float)]: the bits above the first differing one are shared
+      const unsigned long long klo = key_of((double)nextafterf(lof, -INFINITY)), khi = key_of((double)nextafterf(hif, INFINITY));
+      int top = 63 - __clzll((long long)((klo ^ khi) | 1ull));  // highest bit that may differ
+      unsigned long long pref = 0, pmask = 0;                    // decided bits / which bits are decided (below `top`)
+      unsigned k = qa, bucket = ncand;
+      int hi_bit = top;  // undecided bits: [0, hi_bit]
+      while (bucket > 64 && hi_bit >= 0) {
+        const int nb = hi_bit + 1 < 11 ? hi_bit + 1 : 11;
+        const int sh = hi_bit + 1 - nb;
+        for (int i = tid; i < NBIN; i += NT) s.hist[i] = 0;
+        __syncthreads();
+        for (unsigned q = 0; q < own; ++q) {
+          const unsigned long long key = mine[q * NT];
+          if ((key & pmask) == pref) atomicAdd(&s.hist[(unsigned)(key >> sh) & ((1u << nb) - 1u)], 1u);
+        }
+        for (unsigned i = tid; i < novf; i += NT) {
+          const unsigned long long key = s.cand[TCAP * NT + i];
+          if ((key & pmask) == pref) atomicAdd(&s.hist[(unsigned)(key >> sh) & ((1u << nb) - 1u)], 1u);
+        }
+        __syncthreads();
+        const BinHit h = find_bin(s.hist, NBIN, k, s.part, &s.hit);
+        __syncthreads();
+        pref |= (unsigned long long)h.bin << sh;
+        pmask |= (unsigned long long)((1u << nb) - 1u) << sh;
+        k -= h.before;
+        bucket = h.count;
+        hi_bit = sh - 1;
+      }
+      if (hi_bit < 0) {
+        A = 0;  // every remaining bit decided: the bucket holds copies of one key; shared high bits added below
+        if (tid == 0) s.resA = pref;
+      } else {
+        if (tid == 0) s.nsmall = 0;
+        __syncthreads();
+        for (unsigned q = 0; q < own; ++q) {
+          const unsigned long long key = mine[q * NT];
+          if ((key & pmask) == pref) {
+            const unsigned w = atomicAdd(&s.nsmall, 1u);
+            if (w < 64) s.small[w] = key;
+          }
+        }
+        for (unsigned i = tid; i < novf; i += NT) {
+          const unsigned long long key = s.cand[TCAP * NT + i];
+          if ((key & pmask) == pref) {
+            const unsigned w = atomicAdd(&s.nsmall, 1u);
+            if (w < 64) s.small[w] = key;
+          }
+        }
+        __syncthreads();
+        const unsigned m = s.nsmall < 64u ? s.nsmall : 64u;
+        if ((unsigned)tid < m) {
+          const unsigned long long me = s.small[tid];
+          unsigned r = 0;
+          for (unsigned u = 0; u < m; ++u) {
+            const unsigned long long o = s.small[u];
+            r += (o < me) || (o == me && u < (unsigned)tid);
+          }
+          if (r == k) s.resA = me;
+        }
+      }
+      __syncthreads();
+      A = s.resA;
+      if (hi_bit < 0) A |= klo & ~((top >= 63) ? ~0ull : ((2ull << top) - 1ull));  // bits above `top` (shared by all)
+      B = A;
+      if (qb != qa) {  // successor of A in sorted order: A again if copies of A reach rank qb, else the next key
+        if (tid == 0) {
+          s.cle = 0;
+          s.nxt = ~0ull;
+        }
+        __syncthreads();
+        unsigned le = 0;
+        unsigned long long nx = ~0ull;
+        for (unsigned q = 0; q < own; ++q) {
+          const unsigned long long key = mine[q * NT];
+          le += key <= A;
+          if (key > A && key < nx) nx = key;
+        }
+        for (unsigned i = tid; i < novf; i += NT) {
+          const unsigned long long key = s.cand[TCAP * NT + i];
+          le += key <= A;
+          if (key > A && key < nx) nx = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          le += __shfl_xor_sync(FULL, le, o);
+          const unsigned long long t = __shfl_xor_sync(FULL, nx, o);
+          nx = t < nx ? t : nx;
+        }
+        if (lane == 0) {
+          atomicAdd(&s.cle, le);
+          atomicMin(&s.nxt, nx);
+        }
+        __syncthreads();
+        B = (qb < s.cle) ? A : s.nxt;
+      }
+    }
+    if (tid == 0) {
+      if (!good) {
+        const int slot = atomicAdd(fail_count, 1);
+        fail_list[slot] = j;
+      } else {
+        double m = NZ ? 0.0 : nan("");
+        if (count > 0) {
+          const double a = value_of(A), b = value_of(B);
+          m = (count & 1u) ? a : (a + b) / 2.0;
+        }
+        med[j] = m;
+        colmin[j] = s.minkey != ~0ull ? value_of(s.minkey) : INFINITY;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // out[s, j] = alpha * (x[s, j] - med[j] + c) + beta[s]   for columns j0 <= j < j1
 __global__ void __launch_bounds__(256) k_fixup(const double* __restrict__ x, double* __restrict__ out,
                                                int64_t ld, int32_t S, int64_t j0, int64_t j1,
@@ -836,6 +1179,10 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
                                (int)(i == 0 ? sizeof(Stats2Smem) : STATS2_SMEM_ONE));
       if (e != cudaSuccess) return e;
     }
+    e = cudaFuncSetAttribute(k_colstats_one<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats3Smem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_colstats_one<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Stats3Smem));
+    if (e != cudaSuccess) return e;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -851,6 +1198,21 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
   cudaError_t e = launch_fill_u32(d_fail, 0u, 1, st);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
+  static const bool old_one = getenv("PLAIDGPU_COLSTATS_OLD") != nullptr;  // A/B switch: two-bracket kernel for one median
+  if (which != COLSTATS_BOTH && !old_one) {
+    const size_t sm3 = sizeof(Stats3Smem);
+    if (which == COLSTATS_ALL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_one<false>, NT, sm3);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_one<true>, NT, sm3);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > N) grid = N;
+    if (which == COLSTATS_ALL)
+      k_colstats_one<false><<<(unsigned)grid, NT, sm3, st>>>(x, ld, S, N, med_all, colmin, d_fail, d_list);
+    else
+      k_colstats_one<true><<<(unsigned)grid, NT, sm3, st>>>(x, ld, S, N, med_nz, colmin, d_fail, d_list);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else {
   const size_t smem = which == COLSTATS_BOTH ? sizeof(Stats2Smem) : STATS2_SMEM_ONE;
   if (which == COLSTATS_ALL)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colstats_fast<true, false>, NT, smem);
@@ -869,6 +1231,7 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
     k_colstats_fast<true, true><<<(unsigned)grid, NT, smem, st>>>(x, ld, S, N, med_all, med_nz, colmin, d_fail, d_list);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  }
   int nfail = 0;
   e = cudaMemcpyAsync(&nfail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return e;

@@ -327,6 +327,37 @@ def test_normalize_medians_long_columns_single_pass_path(gpu_ctx):
         assert rel_err(pb.normalize_medians(x, ignore_zero=iz, ctx=gpu_ctx), O.normalize_medians(x, ignore_zero=iz)) < 1e-13
     y = rng.normal(size=(30000, 6))              # C4-length columns, no zeros, negatives
     assert rel_err(pb.normalize_medians(y, ctx=gpu_ctx), O.normalize_medians(y)) < 1e-13
+    # single-median kernel (ignore.zero given): its bracket and filter live in FP32 — cases where float rounding,
+    # float range or the zero block could matter
+    S = 30000
+    w = rng.normal(size=(S, 14))
+    w[rng.random(w.shape) < 0.3] = 0.0           # zeros INSIDE the bracket of the non-zero median (centred scores)
+    w[:, 1] = 1.0 + rng.integers(0, 50, size=S) * 2.0 ** -40   # distinct doubles that round to ONE float
+    w[:, 2] = rng.normal(size=S) * 1e-60         # every value rounds to +-0 in float
+    w[:, 3] = rng.normal(size=S) * 1e200         # every value rounds to +-inf in float
+    w[::3, 4] = np.inf; w[1::3, 4] = -np.inf     # infinities on both sides
+    w[:, 5] = np.abs(w[:, 5]); w[:, 5][rng.random(S) < 0.5] = 0.0; w[::11, 5] = 1e-50  # zeros + tiny non-zeros
+    w[:, 6] = 0.0; w[:30, 6] = rng.random(30)    # fewer than 48 valid sample points when the zeros are dropped
+    w[:, 7] = -np.abs(w[:, 7]) - 1.0             # all negative
+    w[:, 8] = np.floor(rng.random(S) * 3.0)      # three values, one of them zero
+    w[:, 9] = rng.random(S) * 2.0 ** -140        # float-subnormal range
+    w[5, 10] = np.nan                            # a single NaN -> exact fallback kernel
+    w[:, 11] = np.where(rng.random(S) < 0.5, 0.0, -0.0)   # signed zeros only
+    w[:, 12] = 3.0 + rng.normal(size=S) * 1e-12  # narrow spread around a float
+    # each column paired with its half (medians m and m / 2 exactly): out = x - m + 0.75 m exposes m at its own scale
+    for k in range(w.shape[1]):
+        pair = np.column_stack([w[:, k], 0.5 * w[:, k]])
+        for iz in (False, True):
+            g, o = pb.normalize_medians(pair, ignore_zero=iz, ctx=gpu_ctx), O.normalize_medians(pair, ignore_zero=iz)
+            fin = np.isfinite(o)
+            assert np.array_equal(np.isfinite(g), fin) and np.array_equal(g[~fin], o[~fin], equal_nan=True), (k, iz)
+            scale = np.max(np.abs(o[fin])) if fin.any() else 0.0
+            assert np.max(np.abs(g[fin] - o[fin]), initial=0.0) <= 1e-13 * scale, (k, iz)
+    with np.errstate(invalid="ignore"):
+        for iz in (False, True):  # all columns in one launch (columns 3 and 4 overflow / poison mean(med): left out)
+            sel = [c for c in range(w.shape[1]) if c not in (3, 4)]
+            assert rel_err(pb.normalize_medians(w[:, sel], ignore_zero=iz, ctx=gpu_ctx),
+                           O.normalize_medians(w[:, sel], ignore_zero=iz)) < 1e-13
 
 
 # ---- reference edge cases ------------------------------------------------------------------------
