@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace plaidgpu {
@@ -1237,6 +1238,8 @@ cudaError_t launch_colstats(const double* x, int64_t ld, int32_t S, int64_t N, d
   if (e != cudaSuccess) return e;
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return e;
+  if (getenv("PLAIDGPU_TRACE_COLSTATS"))
+    fprintf(stderr, "[plaidgpu] colstats: %d of %lld columns redone by the three-pass kernel\n", nfail, (long long)N);
   if (nfail > 0) {
     int64_t g2 = (int64_t)sms * 4;
     if (g2 > nfail) g2 = nfail;

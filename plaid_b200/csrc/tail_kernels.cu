@@ -92,13 +92,32 @@ __global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ 
     double fb = 0.0;
     if (mode >= XF_SING) fb = xform_value(mode, r0 ? r0[j] : 0.0, a0, a1);
     const double sc = 1.0 / colinv[j];  // 2^e_j, exact
-    for (int32_t e = xp[j] + lane; e < xe[j]; e += 32) {
-      const int32_t g = tmap[oi[e]];
-      if (g < 0) continue;
-      double v = xform_value(mode, ox[e], a0, a1);
-      if (mode >= XF_SING) v -= fb;
-      const uint32_t pos = base + rp[g] + atomicAdd(cur + g, 1u);
-      ent[pos] = make_uint2((uint32_t)(int32_t)__double2ll_rn(v * sc), cell);
+    // four iterations at a time, each dependent level (index -> tail row -> row pointer + cursor) issued for all four
+    // before the next: one warp per column has no other way of overlapping the chain
+    const int32_t e1 = xe[j];
+    for (int32_t e0 = xp[j]; e0 < e1; e0 += 128) {
+      int32_t rr[4], gg[4];
+      double xv[4];
+      uint32_t pos[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t e = e0 + 32 * u + lane;
+        const bool in = e < e1;
+        rr[u] = in ? __ldg(oi + e) : -1;
+        xv[u] = in ? __ldg(ox + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gg[u] = rr[u] >= 0 ? __ldg(tmap + rr[u]) : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (gg[u] >= 0) pos[u] = base + rp[gg[u]] + atomicAdd(cur + gg[u], 1u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (gg[u] < 0) continue;
+        double v = xform_value(mode, xv[u], a0, a1);
+        if (mode >= XF_SING) v -= fb;
+        ent[pos[u]] = make_uint2((uint32_t)(int32_t)__double2ll_rn(v * sc), cell);
+      }
     }
   }
 }

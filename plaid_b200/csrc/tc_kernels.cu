@@ -566,14 +566,35 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
     // pass 1: largest |value| among the block entries (and, with a tail pass, the tail entries) of this column
     double mx = 0.0;
     bool bad = false;
-    for (int32_t e = c0 + lane; e < c1; e += 32) {
-      const int32_t r1 = xi[e];
-      if (dmap[r1] != 0xFFFFu || (tmap && tmap[r1] >= 0)) {
-        double v = xform_value(mode, xx[e], a0, a1);
-        if (mode >= XF_SING) v -= fb;
-        const double a = fabs(v);
-        if (!(a <= 1.0e300)) bad = true;  // NaN or Inf
-        mx = fmax(mx, a);
+    // four iterations at a time: the index / value loads of all four are issued first, then the four map gathers —
+    // one warp per column has nothing else to hide the index -> map dependency with
+    for (int32_t e0 = c0; e0 < c1; e0 += 128) {
+      int32_t rr[4];
+      double xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t e = e0 + 32 * u + lane;
+        const bool in = e < c1;
+        rr[u] = in ? __ldg(xi + e) : -1;
+        xv[u] = in ? __ldg(xx + e) : 0.0;
+      }
+      bool use[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t r1 = rr[u] < 0 ? 0 : rr[u];
+        const unsigned d = __ldg(dmap + r1);
+        const int32_t g = tmap ? __ldg(tmap + r1) : -1;
+        use[u] = rr[u] >= 0 && (d != 0xFFFFu || g >= 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (use[u]) {
+          double v = xform_value(mode, xv[u], a0, a1);
+          if (mode >= XF_SING) v -= fb;
+          const double a = fabs(v);
+          if (!(a <= 1.0e300)) bad = true;  // NaN or Inf
+          mx = fmax(mx, a);
+        }
       }
     }
 #pragma unroll
@@ -592,37 +613,49 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
     __syncwarp();
     // pass 2: digits of the block entries, compaction of the rest
     int32_t o = c0;
-    for (int32_t b = c0; b < c1; b += 32) {
-      const int32_t e = b + lane;
-      int32_t r = 0;
-      double x = 0.0;
-      bool keep = false;
-      if (e < c1) {
-        r = xi[e];
-        x = xx[e];
-        const unsigned d = dmap[r];
-        keep = d == 0xFFFFu;
-        if (!keep) {
+    for (int32_t b0 = c0; b0 < c1; b0 += 128) {
+      int32_t rr[4], gg[4];
+      double xv[4];
+      unsigned dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t e = b0 + 32 * u + lane;
+        const bool in = e < c1;
+        rr[u] = in ? __ldg(xi + e) : -1;
+        xv[u] = in ? __ldg(xx + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t r1 = rr[u] < 0 ? 0 : rr[u];
+        dd[u] = __ldg(dmap + r1);
+        gg[u] = tmap ? __ldg(tmap + r1) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + 32 * u >= c1) break;  // warp-uniform
+        const int32_t r = rr[u];
+        const double x = xv[u];
+        const bool in = r >= 0;
+        const bool keep = in && dd[u] == 0xFFFFu;
+        if (in && !keep) {
           double v = xform_value(mode, x, a0, a1);
           if (mode >= XF_SING) v -= fb;
           const long long q = (fabs(v) <= 1.0e300) ? __double2ll_rn(v * sc) : 0ll;
           signed char dg[SLICES];
           digits_of<SLICES>(q, dg);
 #pragma unroll
-          for (int k = 0; k < SLICES; ++k) rows[k * Kp + d] = dg[k];
+          for (int k = 0; k < SLICES; ++k) rows[k * Kp + dd[u]] = dg[k];
         }
-      }
-      const unsigned mk = __ballot_sync(FULL, keep);
-      if (keep) {
-        const int32_t q = o + __popc(mk & lt);
-        oi[q] = r;
-        ox[q] = x;
-        if (tmap) {  // entries per (cell tile, tail row): the gene-major regrouping of tail_kernels.cu
-          const int32_t g = tmap[r];
-          if (g >= 0) atomicAdd(tcnt + (size_t)(j / tileC) * Pt + g, 1u);
+        const unsigned mk = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int32_t q = o + __popc(mk & lt);
+          oi[q] = r;
+          ox[q] = x;
+          // entries per (cell tile, tail row): the gene-major regrouping of tail_kernels.cu
+          if (gg[u] >= 0) atomicAdd(tcnt + (size_t)(j / tileC) * Pt + gg[u], 1u);
         }
+        o += __popc(mk);
       }
-      o += __popc(mk);
     }
     if (lane == 0) xe[j] = o;
     __syncwarp();
