@@ -11,6 +11,8 @@
 // size is P - nnz, which only shifts the ranks of the positive entries.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <math.h>
 
 namespace plaidgpu {
@@ -108,12 +110,48 @@ struct RankParams {
   unsigned long long* ws_keys;  // global workspace (GLOBAL_WS only)
   void* ws_pos;
   int cap;  // shared-memory capacity in elements (!GLOBAL_WS)
+  int ss_max;       // largest splitter count the bucket region holds (0: bucket path off), power of two
+  size_t bucket_off;  // byte offset of the bucket region behind keys + positions
 };
+
+// ---- bucket path (columns with many distinct values) ----------------------------------------------------------
+// Ranks need "how many keys are smaller / equal", not a sorted array.  A strided sample of SS keys is sorted and
+// used as splitters; every key falls either ON a splitter value (an "equal class": all its members are tied, the
+// rank follows from counts alone) or strictly BETWEEN two splitters (an "interval bucket" of ~n / SS keys).  One
+// counting pass + an exclusive scan give each class its first position; the members of every interval bucket are
+// listed (unordered: atomics) and each key counts the smaller / equal keys inside its own bucket — a segmented
+// MSD pass with data-dependent splitters followed by direct ranking, ~3 binary searches + ~n / SS compares per key
+// instead of the log^2(n) / 2 compare-exchange stages of a bitonic network.  Large tie classes are caught by the
+// sample (a class holding 1 % of the column is missed by 1,024 samples with probability 3e-5); a column whose
+// largest interval bucket still exceeds BUCKET_MAX is sorted by the network instead.
+constexpr int BUCKET_MIN_N = 256;   // shorter columns: the network is cheap
+constexpr int BUCKET_MAX = 1024;    // largest interval bucket ranked directly
+
+__device__ void sort_keys_pow2(unsigned long long* k, int n) {  // all threads; n = power of two
+  for (int size = 2; size <= n; size <<= 1) {
+    const int hs = size >> 1;
+    for (int q = threadIdx.x; q < n / 2; q += blockDim.x) {
+      const int o = q & (hs - 1), base = (q & ~(hs - 1)) << 1;
+      const int i = base + o, l = base + size - 1 - o;
+      const unsigned long long a = k[i], b = k[l];
+      if (a > b) { k[i] = b; k[l] = a; }
+    }
+    __syncthreads();
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+      for (int q = threadIdx.x; q < n / 2; q += blockDim.x) {
+        const int i = ((q & ~(stride - 1)) << 1) | (q & (stride - 1)), l = i + stride;
+        const unsigned long long a = k[i], b = k[l];
+        if (a > b) { k[i] = b; k[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
 
 template <typename PosT, bool GLOBAL_WS>
 __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
   extern __shared__ unsigned long long rsm[];
-  __shared__ int s_nnan;
+  __shared__ int s_nnan, s_bmax, s_zneg, s_zs;
   __shared__ double s_max[RT / 32];
   // the fast path's tables share the dynamic buffer with the sort path's keys / positions (it is done, or has
   // given up, before those are written)
@@ -263,6 +301,176 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
     }
     if (my_nan) atomicAdd(&s_nnan, my_nan);
     __syncthreads();
+    bool bucket_done = false;
+    if (!GLOBAL_WS && p.ss_max >= 32 && n >= BUCKET_MIN_N) {
+      // ---- bucket path: splitters from a sorted sample, counting, direct ranking inside the interval buckets ----
+      int SS = 32;
+      while (SS * 32 <= n && SS < p.ss_max) SS <<= 1;
+      unsigned long long* const sp = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(rsm) + p.bucket_off);
+      unsigned* const cnt = reinterpret_cast<unsigned*>(sp + SS);  // code = 2 * b + eq, b = #splitters below the key
+      unsigned* const base = cnt + (2 * SS + 2);
+      unsigned* const part = base + (2 * SS + 2);                   // RT partial sums
+      const int ncode = 2 * SS + 1;
+      for (int i = tid; i < SS; i += RT) sp[i] = keys[(int)(((int64_t)i * n) / SS)];
+      for (int i = tid; i < ncode + 1; i += RT) cnt[i] = 0u;
+      if (tid == 0) s_bmax = 0;
+      __syncthreads();
+      sort_keys_pow2(sp, SS);
+      auto code_of = [&](unsigned long long key) {
+        const int b = lower_bound(sp, SS, key);
+        return 2 * b + ((b < SS && sp[b] == key) ? 1 : 0);
+      };
+      for (int l = tid; l < n; l += RT) {
+        const unsigned long long key = keys[l];
+        if (key != NAN_KEY) atomicAdd(&cnt[code_of(key)], 1u);
+      }
+      __syncthreads();
+      {  // exclusive scan of the class sizes in value order; cnt becomes the cursors of the interval buckets
+        const int per = (ncode + RT - 1) / RT, a = min(ncode, tid * per), b = min(ncode, a + per);
+        unsigned sum = 0, bm = 0;
+        for (int i = a; i < b; ++i) {
+          sum += cnt[i];
+          if (!(i & 1)) bm = max(bm, cnt[i]);
+        }
+        part[tid] = sum;
+        if (bm) atomicMax(&s_bmax, (int)bm);
+        __syncthreads();
+        if (tid < 32) {
+          unsigned loc = 0;
+#pragma unroll
+          for (int i = 0; i < RT / 32; ++i) loc += part[tid * (RT / 32) + i];
+          unsigned incl = loc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, incl, o);
+            if (tid >= o) incl += t;
+          }
+          unsigned run = incl - loc;
+          for (int i = 0; i < RT / 32; ++i) {
+            const unsigned t = part[tid * (RT / 32) + i];
+            part[tid * (RT / 32) + i] = run;
+            run += t;
+          }
+        }
+        __syncthreads();
+        unsigned run = part[tid];
+        for (int i = a; i < b; ++i) {
+          const unsigned t = cnt[i];
+          base[i] = run;
+          cnt[i] = 0u;
+          run += t;
+        }
+        if (tid == RT - 1) base[ncode] = run;  // == number of valid keys (threads past the end carry the total)
+      }
+      __syncthreads();
+      if (s_bmax <= BUCKET_MAX) {  // block-uniform
+        for (int l = tid; l < n; l += RT) {  // member lists of all classes (order inside a class is irrelevant)
+          const unsigned long long key = keys[l];
+          if (key == NAN_KEY) {
+            p.rank[c0 + l] = nan("");
+            continue;
+          }
+          const int c = code_of(key);
+          pos[base[c] + atomicAdd(&cnt[c], 1u)] = (PosT)l;
+        }
+        const int nv = n - s_nnan;
+        int zimp = 0;
+        if (p.dense_sem) {  // zero group (dense semantics): stored zeros + implicit zeros
+          if (tid == 0) {
+            const int c = code_of(ZERO_KEY);
+            if (c & 1) {
+              s_zneg = (int)base[c];
+              s_zs = (int)(base[c + 1] - base[c]);
+            } else {
+              s_zneg = -1 - c;  // no stored zero on a splitter: counted inside interval bucket c below
+              s_zs = 0;
+            }
+          }
+          zimp = p.P - n;
+        }
+        __syncthreads();
+        if (p.dense_sem && s_zneg < 0) {
+          const int c = -1 - s_zneg;
+          __syncthreads();
+          if (tid < 32) {
+            int less = 0, eq = 0;
+            for (unsigned q = base[c] + tid; q < base[c + 1]; q += 32) {
+              const unsigned long long k2 = keys[pos[q]];
+              less += k2 < ZERO_KEY;
+              eq += k2 == ZERO_KEY;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              less += __shfl_xor_sync(FULL, less, o);
+              eq += __shfl_xor_sync(FULL, eq, o);
+            }
+            if (tid == 0) {
+              s_zneg = (int)base[c] + less;
+              s_zs = eq;
+            }
+          }
+          __syncthreads();
+        }
+        if (p.dense_sem) {
+          nneg = s_zneg;
+          z = s_zs + zimp;
+        } else {
+          nneg = 0;
+          z = 0;
+        }
+        // one thread per SLOT of the class-ordered list: the lanes of a warp sit in the same one or two buckets, so
+        // their member loops have the same length and read the same addresses (broadcast)
+        for (int q = tid; q < nv; q += RT) {
+          const int l = (int)pos[q];
+          const unsigned long long key = keys[l];
+          int first, last;
+          if (p.dense_sem && key == ZERO_KEY) {
+            first = nneg;
+            last = nneg + z;
+          } else {
+            int lo = 0, hi = ncode + 1;  // class of slot q: base[c] <= q < base[c + 1]
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (base[mid] <= (unsigned)q) lo = mid + 1; else hi = mid;
+            }
+            const int c = lo - 1;
+            if (c & 1) {
+              first = (int)base[c];
+              last = (int)base[c + 1];
+            } else {
+              int less = 0, eq = 0;
+              const unsigned q1 = base[c + 1];
+#pragma unroll 4
+              for (unsigned q2 = base[c]; q2 < q1; ++q2) {
+                const unsigned long long k2 = keys[pos[q2]];
+                less += k2 < key;
+                eq += k2 == key;
+              }
+              first = (int)base[c] + less;
+              last = first + eq;
+            }
+            if (p.dense_sem && key > ZERO_KEY) {
+              first += zimp;
+              last += zimp;
+            }
+          }
+          double r = p.ties == PLAIDGPU_TIES_AVERAGE ? 0.5 * (double)(first + 1 + last)
+                     : p.ties == PLAIDGPU_TIES_MIN   ? (double)(first + 1)
+                                                     : (double)last;
+          if (p.is_signed) {
+            const double v = p.xx[c0 + l];
+            r = v > 0.0 ? r : (v < 0.0 ? -r : 0.0);
+          }
+          mymax = fmax(mymax, fabs(r));
+          p.rank[c0 + l] = r;
+        }
+        bucket_done = true;
+      } else {
+        for (int l = tid; l < n; l += RT) pos[l] = (PosT)l;  // the network needs the identity positions back
+      }
+      __syncthreads();
+    }
+    if (!bucket_done) {
     bitonic_sort<PosT>(keys, pos, n);
     const int nv = n - s_nnan;  // NaN sorted last
     // zero group (dense semantics): stored zeros + implicit zeros
@@ -303,6 +511,7 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
       }
       p.rank[c0 + pos[q]] = r;
     }
+    }  // !bucket_done
     }  // !fast_done
     double rz = 0.0;
     if (p.dense_sem && z > 0 && !p.is_signed) {
@@ -417,9 +626,21 @@ cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t per = sizeof(unsigned long long) + sizeof(PosT);
-  int cap = (max_n + 1) & ~1;  // keep the pos array 8-byte aligned behind the keys
-  if (cap < 2) cap = 2;
+  int cap = (max_n + 3) & ~3;  // keep the pos array and the bucket region 8-byte aligned behind the keys
+  if (cap < 4) cap = 4;
   size_t need = (size_t)cap * per;
+  // bucket region behind keys + positions: SS splitters, 2 x (2 SS + 2) counters, RT partial sums
+  auto bucket_bytes = [](int ss) { return (size_t)ss * 8 + 2 * (size_t)(2 * ss + 2) * 4 + (size_t)RT * 4; };
+  int ss = 0;
+  if (max_n >= BUCKET_MIN_N && !getenv("PLAIDGPU_RANK_NETWORK")) {
+    ss = 32;
+    while (ss * 32 <= max_n && ss < 1024) ss <<= 1;
+    while (ss >= 32 && need + bucket_bytes(ss) + 2048 > (size_t)smem_optin) ss >>= 1;  // a coarser split still beats the network
+    if (ss < 32) ss = 0;
+  }
+  p.ss_max = ss;
+  p.bucket_off = need;
+  if (ss) need += bucket_bytes(ss);
   if (need < sizeof(RankFast)) need = sizeof(RankFast);
   cudaError_t e;
   if (need + 2048 <= (size_t)smem_optin) {

@@ -289,6 +289,51 @@ def test_colranks_counting_and_sorting_paths_agree(gpu_ctx):
     same(pb.colranks(D, ctx=gpu_ctx), O.colranks(D))
 
 
+def test_colranks_bucket_path_many_distinct_values(gpu_ctx):
+    """columns with many distinct values are ranked by the splitter / bucket path of k_rank (no sort): dense bulk
+    columns of 20,000 distinct values, mixtures of large tie classes and distinct values, signed ranks, dense
+    semantics with negatives where the zero group falls on / between splitters, NaN, long sparse columns"""
+    rng = np.random.default_rng(33)
+    P = 20000
+    D = rng.normal(size=(P, 9))
+    D[:, 1] = np.abs(D[:, 1]); D[rng.random(P) < 0.2, 1] = 0.0         # bulk column with 20 % zeros (a big tie class)
+    D[:, 2] = np.where(rng.random(P) < 0.5, np.round(D[:, 2], 1), D[:, 2])  # half heavily tied, half distinct
+    D[::97, 3] = np.nan
+    D[:, 4] = np.exp(8.0 * D[:, 4])                                     # skewed over many binades
+    D[:, 5] = 1.0 + rng.integers(0, 3000, size=P) * 2.0 ** -45          # 3000 classes differing in the low bits only
+    D[:, 6] = np.sort(D[:, 6])                                          # sorted input: the strided sample is exact quantiles
+    D[:, 7] = -np.abs(D[:, 7])
+    D[:, 8] = np.concatenate([np.full(P - 300, 2.5), rng.normal(size=300)])  # one class holds 98.5 %
+
+    def same(a, b):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+    for ties in ("average", "min", "max"):
+        for signed in (False, True):
+            same(pb.colranks(D, signed=signed, ties_method=ties, ctx=gpu_ctx), O.colranks(D, signed=signed, ties_method=ties))
+    # sparse columns of ~5,000 distinct stored values each, with negatives, stored zeros and NaN: sparse_colranks and
+    # the dense-semantics ranks (implicit zeros form one group between the negative and the positive entries)
+    n = 5000
+    cols = []
+    for k in range(6):
+        rows = np.sort(rng.choice(P, size=n, replace=False))
+        vals = rng.normal(size=n)
+        if k == 1: vals = np.abs(vals)
+        if k == 2: vals[:40] = 0.0
+        if k == 3: vals[:7] = np.nan
+        if k == 4: vals = -np.abs(vals)
+        if k == 5: vals[::2] = np.round(vals[::2], 2)
+        cols.append((rows, vals))
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r, _ in cols])])
+    X = sp.csc_matrix((np.concatenate([v for _, v in cols]), np.concatenate([r for r, _ in cols]), indptr), shape=(P, len(cols)))
+    for ties in ("average", "min", "max"):
+        for signed in (False, True):
+            same(pb.sparse_colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx).data,
+                 O.sparse_colranks(X, signed=signed, ties_method=ties).data)
+            same(pb.colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx), O.colranks(X, signed=signed, ties_method=ties))
+
+
 # ---- normalize_medians ---------------------------------------------------------------------------
 def test_normalize_medians_edge_cases(gpu_ctx):
     rng = np.random.default_rng(4)
