@@ -19,7 +19,8 @@ namespace plaidgpu {
 
 namespace {
 
-constexpr int RT = 256;
+constexpr int RT_SHORT = 256;  // threads per column CTA, short columns
+constexpr int RT_MAX = 1024;  // long columns (one CTA per SM by shared memory): more warps to hide the latencies
 constexpr unsigned long long ZERO_KEY = 0x8000000000000000ull;
 constexpr unsigned long long NAN_KEY = ~0ull;
 
@@ -82,9 +83,12 @@ __device__ __forceinline__ int upper_bound(const unsigned long long* k, int n, u
 // multiplicities, only those (<= RANK_DCAP) are sorted, a prefix sum over the multiplicities gives
 // every value its tie run [first, last), and every entry looks its rank up.  Columns with more
 // distinct values fall through to the bitonic sort below; both paths produce the same integers.
-constexpr int RANK_HT = 1024;    // hash slots
+// hash slots: every thread may insert one new key after the distinct-value limit was last seen below the cap, so the
+// table must hold RANK_DCAP + (threads per CTA) keys with room to probe: 1,024 slots for 256 threads, 2,048 for 1,024
+template <bool WIDE> struct RankHt { static constexpr int value = WIDE ? 2048 : 1024; };
 constexpr int RANK_DCAP = 448;   // distinct values the fast path accepts (table at most ~70 % full while racing)
 constexpr int RANK_DMAX = 512;
+template <int RANK_HT>
 struct RankFast {
   unsigned long long tab[RANK_HT];
   unsigned cnt[RANK_HT];
@@ -94,8 +98,9 @@ struct RankFast {
   int first[RANK_DMAX];
   int ndist, m;
 };
+template <int RANK_HT>
 __device__ __forceinline__ unsigned rank_hash(unsigned long long key) {
-  return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 54);  // top 10 bits
+  return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> (RANK_HT == 2048 ? 53 : 54));  // top 11 / 10 bits
 }
 
 struct RankParams {
@@ -148,14 +153,16 @@ __device__ void sort_keys_pow2(unsigned long long* k, int n) {  // all threads; 
   }
 }
 
-template <typename PosT, bool GLOBAL_WS>
-__global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
+template <typename PosT, bool GLOBAL_WS, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankParams p) {
+  constexpr int RT = WIDE ? RT_MAX : RT_SHORT;  // 256 (several short columns per SM) or 1024 (one long column per SM)
   extern __shared__ unsigned long long rsm[];
   __shared__ int s_nnan, s_bmax, s_zneg, s_zs;
   __shared__ double s_max[RT / 32];
   // the fast path's tables share the dynamic buffer with the sort path's keys / positions (it is done, or has
   // given up, before those are written)
-  RankFast& sf = *reinterpret_cast<RankFast*>(rsm);
+  constexpr int RANK_HT = RankHt<WIDE>::value;
+  RankFast<RANK_HT>& sf = *reinterpret_cast<RankFast<RANK_HT>*>(rsm);
   const int tid = threadIdx.x;
 
   for (int64_t j = blockIdx.x; j < p.N; j += gridDim.x) {
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
         }
         if (*reinterpret_cast<volatile int*>(&sf.ndist) > RANK_DCAP) break;  // too many distinct values: give up early
         const unsigned long long key = key_of(p.is_signed ? fabs(v) : v);
-        unsigned h = rank_hash(key);
+        unsigned h = rank_hash<RANK_HT>(key);
         for (;;) {
           const unsigned long long old = atomicCAS(&sf.tab[h], NAN_KEY, key);
           if (old == NAN_KEY) atomicAdd(&sf.ndist, 1);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
             r = nan("");
           } else {
             const unsigned long long key = key_of(p.is_signed ? fabs(v) : v);
-            unsigned h = rank_hash(key);
+            unsigned h = rank_hash<RANK_HT>(key);
             while (sf.tab[h] != key) h = (h + 1) & (RANK_HT - 1);
             r = sf.rk[h];
             if (p.is_signed) r = v > 0.0 ? r : (v < 0.0 ? -r : 0.0);
@@ -305,7 +312,9 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
     if (!GLOBAL_WS && p.ss_max >= 32 && n >= BUCKET_MIN_N) {
       // ---- bucket path: splitters from a sorted sample, counting, direct ranking inside the interval buckets ----
       int SS = 32;
-      while (SS * 32 <= n && SS < p.ss_max) SS <<= 1;
+      // keys per interval bucket: 8-16 where the CTA owns the SM anyway, 32-64 for short columns (a larger bucket
+      // region would cost the common tied-column path its occupancy)
+      while (SS * (WIDE ? 8 : 32) <= n && SS < p.ss_max) SS <<= 1;
       unsigned long long* const sp = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(rsm) + p.bucket_off);
       unsigned* const cnt = reinterpret_cast<unsigned*>(sp + SS);  // code = 2 * b + eq, b = #splitters below the key
       unsigned* const base = cnt + (2 * SS + 2);
@@ -337,7 +346,6 @@ __global__ void __launch_bounds__(RT) k_rank(const RankParams p) {
         __syncthreads();
         if (tid < 32) {
           unsigned loc = 0;
-#pragma unroll
           for (int i = 0; i < RT / 32; ++i) loc += part[tid * (RT / 32) + i];
           unsigned incl = loc;
 #pragma unroll
@@ -630,29 +638,35 @@ cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_
   if (cap < 4) cap = 4;
   size_t need = (size_t)cap * per;
   // bucket region behind keys + positions: SS splitters, 2 x (2 SS + 2) counters, RT partial sums
-  auto bucket_bytes = [](int ss) { return (size_t)ss * 8 + 2 * (size_t)(2 * ss + 2) * 4 + (size_t)RT * 4; };
+  const bool wide = max_n >= 8192;  // long columns: <= 2 CTAs per SM by shared memory anyway, so wide CTAs
+  const int threads = wide ? RT_MAX : RT_SHORT;
+  auto bucket_bytes = [threads](int ss) { return (size_t)ss * 8 + 2 * (size_t)(2 * ss + 2) * 4 + (size_t)threads * 4; };
   int ss = 0;
   if (max_n >= BUCKET_MIN_N && !getenv("PLAIDGPU_RANK_NETWORK")) {
     ss = 32;
-    while (ss * 32 <= max_n && ss < 1024) ss <<= 1;
+    while (ss * (wide ? 8 : 32) <= max_n && ss < 1024) ss <<= 1;
     while (ss >= 32 && need + bucket_bytes(ss) + 2048 > (size_t)smem_optin) ss >>= 1;  // a coarser split still beats the network
     if (ss < 32) ss = 0;
   }
   p.ss_max = ss;
   p.bucket_off = need;
   if (ss) need += bucket_bytes(ss);
-  if (need < sizeof(RankFast)) need = sizeof(RankFast);
+  if (need < sizeof(RankFast<1024>)) need = sizeof(RankFast<1024>);
+  if (wide && need < sizeof(RankFast<2048>)) need = sizeof(RankFast<2048>);
   cudaError_t e;
   if (need + 2048 <= (size_t)smem_optin) {
     p.cap = cap;
-    e = cudaFuncSetAttribute(k_rank<PosT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    const void* fn = wide ? (const void*)k_rank<PosT, false, true> : (const void*)k_rank<PosT, false, false>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rank<PosT, false>, RT, need);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, need);
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (grid > p.N) grid = p.N;
-    k_rank<PosT, false><<<(unsigned)grid, RT, need, st>>>(p);
+    void* args[] = {(void*)&p};
+    e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(threads), args, need, st);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
   }
   // column does not fit in shared memory: sort in a global workspace (slow path)
@@ -666,7 +680,7 @@ cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_
   p.ws_pos = wp;
   int64_t grid = (int64_t)sm_count() * 4;
   if (grid > p.N) grid = p.N;
-  k_rank<PosT, true><<<(unsigned)grid, RT, 0, st>>>(p);
+  k_rank<PosT, true, false><<<(unsigned)grid, RT_SHORT, 0, st>>>(p);
   e = cudaGetLastError();
   cudaFreeAsync(wk, st);
   cudaFreeAsync(wp, st);
