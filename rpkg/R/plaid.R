@@ -37,7 +37,7 @@
   }
 }
 
-.score <- function(X, matG, opts) {
+.score <- function(X, matG, opts, y = NULL) {
   x <- .as_x(X)
   rn <- x$dimnames[[1]]
   gg <- intersect(rn, rownames(matG))                                 # R/plaid.R:65
@@ -51,6 +51,12 @@
   rowmap[is.na(rowmap) | duplicated(rn)] <- -1L
   G <- methods::as(matG, "CsparseMatrix")
   if (!inherits(G, "dgCMatrix")) G <- methods::as(methods::as(G, "dMatrix"), "generalMatrix")
+  if (!is.null(y)) {  # plaid.test("lm"): scores reduced per set and sample group on the device, S x 4 back
+    out <- .Call(C_plaidgpu_score_group_moments, .ctxs(), x$kind, x$p, x$i, x$x, as.integer(x$dim),
+                 G@p, G@i, G@x, as.integer(dim(G)), as.integer(rowmap), opts, as.integer(y))
+    rownames(out) <- colnames(matG)
+    return(out)
+  }
   out <- .Call(C_plaidgpu_score, .ctxs(), x$kind, x$p, x$i, x$x, as.integer(x$dim),
                G@p, G@i, G@x, as.integer(dim(G)), as.integer(rowmap), opts)
   dimnames(out) <- list(colnames(matG), x$dimnames[[2]])
@@ -169,11 +175,13 @@ plaid.test <- function(X, y, G, gsetX, tests = c("one", "two", "lm"),
     ff$two <- mean1 - mean0
   }
   if ("lm" %in% tests) {
-    if (is.null(gsetX)) {
+    if (missing(gsetX) || is.null(gsetX)) {
+      ## the S x N score matrix is never materialised for the host: plaid() and the group sums run as one device call
       message("[plaid.test] computing plaid scores...")
-      gsetX <- plaid(X, G)
+      gm <- .score(X, G, list(scorer = 0L, stats_mean = 1L, normalize = 1L), y = y)
+    } else {
+      gm <- .Call(C_plaidgpu_group_moments, .ctx(), as.matrix(gsetX), as.integer(y))
     }
-    gm <- .Call(C_plaidgpu_group_moments, .ctx(), gsetX, as.integer(y))
     m0 <- gm[, 1] / n0; m1 <- gm[, 3] / n1
     v0 <- (gm[, 2] - n0 * m0^2) / (n0 - 1); v1 <- (gm[, 4] - n1 * m1^2) / (n1 - 1)
     fac <- v0 / n0 + v1 / n1

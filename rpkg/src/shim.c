@@ -58,6 +58,26 @@ static void fill_matrix(plaidgpu_matrix* M, int kind, SEXP p, SEXP i, SEXP x, SE
   M->x = REAL(x);
 }
 
+/* named list of options from R -> plaidgpu_opts (defaults for whatever is absent) */
+static void fill_opts(plaidgpu_opts* op, SEXP opts) {
+  plaidgpu_opts o;
+  plaidgpu_default_opts(&o);
+  o.scorer = opt_int(opts, "scorer", o.scorer);
+  o.stats_mean = opt_int(opts, "stats_mean", o.stats_mean);
+  o.normalize = opt_int(opts, "normalize", o.normalize);
+  o.remove_log2 = opt_int(opts, "remove_log2", o.remove_log2);
+  o.score_mean = opt_int(opts, "score_mean", o.score_mean);
+  o.alpha = opt_dbl(opts, "alpha", o.alpha);
+  o.rmax = opt_dbl(opts, "rmax", o.rmax);
+  o.auc_max_rank = opt_dbl(opts, "auc_max_rank", o.auc_max_rank);
+  o.tau = opt_dbl(opts, "tau", o.tau);
+  o.gsva_ecdf = opt_int(opts, "gsva_ecdf", 0);
+  o.nrow_x = (int64_t)opt_dbl(opts, "nrow_x", 0.0);
+  SEXP csums = list_get(opts, "matg_full_colsums");
+  o.matg_full_colsums = csums == R_NilValue ? NULL : REAL(csums);
+  *op = o;
+}
+
 /* plaid() and the replaid.* scorers.  `ctx` is one context (external pointer) or a list of contexts on different
  * devices (options(plaid.gpus = n) in R/plaid.R): the columns are then split over them by plaidgpu_score_multi, one
  * host thread per device inside the library, the shards landing directly in the result matrix. */
@@ -83,20 +103,7 @@ SEXP C_plaidgpu_score(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim,
   plaidgpu_matrix M;
   fill_matrix(&M, Rf_asInteger(kind), Xp, Xi, Xx, Xdim);
   plaidgpu_opts o;
-  plaidgpu_default_opts(&o);
-  o.scorer = opt_int(opts, "scorer", o.scorer);
-  o.stats_mean = opt_int(opts, "stats_mean", o.stats_mean);
-  o.normalize = opt_int(opts, "normalize", o.normalize);
-  o.remove_log2 = opt_int(opts, "remove_log2", o.remove_log2);
-  o.score_mean = opt_int(opts, "score_mean", o.score_mean);
-  o.alpha = opt_dbl(opts, "alpha", o.alpha);
-  o.rmax = opt_dbl(opts, "rmax", o.rmax);
-  o.auc_max_rank = opt_dbl(opts, "auc_max_rank", o.auc_max_rank);
-  o.tau = opt_dbl(opts, "tau", o.tau);
-  o.gsva_ecdf = opt_int(opts, "gsva_ecdf", 0);
-  o.nrow_x = (int64_t)opt_dbl(opts, "nrow_x", 0.0);
-  SEXP csums = list_get(opts, "matg_full_colsums");
-  o.matg_full_colsums = csums == R_NilValue ? NULL : REAL(csums);
+  fill_opts(&o, opts);
   o.out_location = PLAIDGPU_HOST;
   R_CheckUserInterrupt(); /* before the (blocking) device call; the library itself never touches the R API */
   /* S x N may exceed 2^31 elements: Rf_allocMatrix takes ints for the dims, the product is R_xlen_t */
@@ -183,12 +190,37 @@ SEXP C_plaidgpu_group_moments(SEXP ctx, SEXP x, SEXP y) {
   return out;
 }
 
+/* plaid.test(tests = "lm") without gsetX (R/plaid.R:423-431): plaid() fused with the per-set group reductions —
+ * the S x N scores stay on the device, an S x 4 matrix (sum0, sumsq0, sum1, sumsq1) comes back */
+SEXP C_plaidgpu_score_group_moments(SEXP ctx, SEXP kind, SEXP Xp, SEXP Xi, SEXP Xx, SEXP Xdim, SEXP Gp, SEXP Gi, SEXP Gx,
+                                    SEXP Gdim, SEXP rowmap, SEXP opts, SEXP y) {
+  plaidgpu_ctx* c = get_ctx(TYPEOF(ctx) == VECSXP ? VECTOR_ELT(ctx, 0) : ctx);
+  const int PG = INTEGER(Gdim)[0], S = INTEGER(Gdim)[1];
+  if (plaidgpu_set_genesets(c, PG, S, INTEGER(Gp), INTEGER(Gi), REAL(Gx)) != PLAIDGPU_OK)
+    Rf_error("plaidgpu_set_genesets: %s", plaidgpu_last_error(c));
+  plaidgpu_matrix M;
+  fill_matrix(&M, Rf_asInteger(kind), Xp, Xi, Xx, Xdim);
+  if ((int64_t)XLENGTH(y) != M.N) Rf_error("plaidgpu: length(y) must equal ncol(X)");
+  plaidgpu_opts o;
+  fill_opts(&o, opts);
+  R_CheckUserInterrupt();
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, S, 4));
+  int rc = plaidgpu_score_group_moments(c, &M, INTEGER(rowmap), &o, INTEGER(y), REAL(out));
+  if (rc != PLAIDGPU_OK) {
+    UNPROTECT(1);
+    Rf_error("plaidgpu_score_group_moments: %s", plaidgpu_last_error(c));
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_plaidgpu_ctx", (DL_FUNC)&C_plaidgpu_ctx, 1},
     {"C_plaidgpu_score", (DL_FUNC)&C_plaidgpu_score, 12},
     {"C_plaidgpu_normalize_medians", (DL_FUNC)&C_plaidgpu_normalize_medians, 3},
     {"C_plaidgpu_colranks", (DL_FUNC)&C_plaidgpu_colranks, 9},
     {"C_plaidgpu_group_moments", (DL_FUNC)&C_plaidgpu_group_moments, 3},
+    {"C_plaidgpu_score_group_moments", (DL_FUNC)&C_plaidgpu_score_group_moments, 13},
     {"C_plaidgpu_crossprod", (DL_FUNC)&C_plaidgpu_crossprod, 11},
     {NULL, NULL, 0}};
 
