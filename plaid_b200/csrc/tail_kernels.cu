@@ -205,12 +205,28 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32, 1) k_tail(const TailParams p)
         rec = make_uint2(0u, 0xFFFFu);
         if ((uint32_t)lane < nk) rec = __ldg(ent + pk + lane);
       };
+      auto seg = [&](uint32_t off, uint32_t nk, uint32_t pk) {
+        uint2 r = make_uint2(0u, 0xFFFFu);
+        if (off + lane < nk) r = __ldg(ent + pk + off + lane);
+        return r;
+      };
       auto member = [&](const uint2 rec, uint32_t nk, uint32_t pk) {
+        if (nk <= 32u) {  // warp-uniform
+          add(rec);
+          return;
+        }
+        // long row (a highly expressed gene in few sets): its entries are one contiguous stream — three segments in
+        // flight while three are added, so the L2 latency is paid once per 96 entries instead of once per 32
+        uint2 q1 = seg(32u, nk, pk), q2 = seg(64u, nk, pk), q3 = seg(96u, nk, pk);
         add(rec);
-        for (uint32_t off = 32; off < nk; off += 32) {  // long rows: further segments
-          uint2 r2 = make_uint2(0u, 0xFFFFu);
-          if (off + lane < nk) r2 = __ldg(ent + pk + off + lane);
-          add(r2);
+        for (uint32_t off = 32; off < nk; off += 96) {
+          const uint2 a = q1, b = q2, c = q3;
+          q1 = seg(off + 96u, nk, pk);
+          q2 = seg(off + 128u, nk, pk);
+          q3 = seg(off + 160u, nk, pk);
+          add(a);
+          if (off + 32u < nk) add(b);
+          if (off + 64u < nk) add(c);
         }
       };
       uint2 e0, e1, e2, e3;

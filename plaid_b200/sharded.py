@@ -239,7 +239,9 @@ def score_shard(ctx, comm, M: L.Matrix, rowmap: np.ndarray, opts: L.Opts, out_pt
     lib = ctx.lib
     local = L.Scalars()
     ctx.check(lib.plaidgpu_score_begin(ctx.h, C.byref(M), rowmap.ctypes.data, C.byref(opts), C.byref(local)))
-    scal = combine_scalars(comm, local)
+    # plaid() itself has no cross-shard scalar before the scores exist (x_min / x_max feed scse's removeLog2 switch,
+    # rank_max the rank scorers): no collective, no host sync on its critical path
+    scal = local if opts.scorer == L.PLAID else combine_scalars(comm, local)
     ctx.check(lib.plaidgpu_score_compute(ctx.h, C.byref(scal), out_ptr))
     needs_norm = (opts.scorer in (L.SSGSEA, L.UCELL, L.AUCELL, L.GSVA)) or (opts.scorer == L.PLAID and opts.normalize)
     if needs_norm:
