@@ -67,6 +67,12 @@ extern "C" {
 #define PLAIDGPU_TIES_AVERAGE 0
 #define PLAIDGPU_TIES_MIN 1
 #define PLAIDGPU_TIES_MAX 2
+/* order-of-appearance methods of base::rank / matrixStats::colRanks: stored-entry ranks (keep_zero = 1) and dense input
+ * only — sparseMatrixStats::colRanks (sparse input, keep_zero = 0) knows max / average / min alone.  "random" draws from
+ * R's RNG and stays an error. */
+#define PLAIDGPU_TIES_FIRST 3
+#define PLAIDGPU_TIES_LAST 4
+#define PLAIDGPU_TIES_DENSE 5 /* matrixStats only: consecutive ranks of the distinct values */
 
 typedef struct plaidgpu_ctx plaidgpu_ctx;
 

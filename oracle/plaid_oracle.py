@@ -47,7 +47,8 @@ def _as_csc(m) -> sp.csc_matrix:
 # base::rank / matrixStats::colRanks / sparseMatrixStats::colRanks semantics
 # ----------------------------------------------------------------------------------
 def rank_vector(v: np.ndarray, ties: str = "average") -> np.ndarray:
-    """base::rank(v, ties.method=ties, na.last="keep") for ties in {average,min,max}.
+    """base::rank(v, ties.method=ties, na.last="keep") for ties in {average,min,max,first,last} and the "dense"
+    method of matrixStats::colRanks.
 
     Explicit stable-sort + tie-run pass (the second implementation, scipy.stats.rankdata,
     lives in tests/test_oracle.py).  Ties are exact fp64 equality (-0 == +0); NaN -> NaN and
@@ -75,7 +76,13 @@ def rank_vector(v: np.ndarray, ties: str = "average") -> np.ndarray:
         r = (start[run] + 1).astype(np.float64)
     elif ties == "max":
         r = end[run].astype(np.float64)
-    else:
+    elif ties == "first":  # ties in order of appearance: the stable order itself
+        r = np.arange(1, n + 1, dtype=np.float64)
+    elif ties == "last":  # ... in reverse order of appearance
+        r = (start[run] + end[run] - np.arange(n)).astype(np.float64)
+    elif ties == "dense":  # matrixStats::colRanks only: consecutive ranks of the distinct values
+        r = (run + 1).astype(np.float64)
+    else:  # "random" draws from R's RNG
         raise ValueError(f"unsupported ties.method {ties!r}")
     res = np.empty(n)
     res[o] = r

@@ -13,7 +13,7 @@ import os
 HOST, DEVICE = 0, 1
 CSC, DENSE = 0, 1
 PLAID, SCSE, SING, SSGSEA, UCELL, AUCELL, GSVA = range(7)
-TIES = {"average": 0, "min": 1, "max": 2}
+TIES = {"average": 0, "min": 1, "max": 2, "first": 3, "last": 4, "dense": 5}
 ROWTF_Z, ROWTF_ECDF, ROWTF_DONE = 0, 1, 2
 FILE_RAW, FILE_NPY = 0, 1
 

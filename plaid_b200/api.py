@@ -360,8 +360,8 @@ def normalize_medians(x, ignore_zero: Optional[bool] = None, *, ctx=None):
 def sparse_colranks(X, signed: bool = False, ties_method: str = "average", *, ctx=None):
     """`sparse_colranks(X, signed, ties.method)` (R/plaid.R:631-650): csc_matrix, same pattern."""
     ctx = ctx or default_context()
-    if ties_method not in L.TIES:
-        raise ValueError(f"ties.method {ties_method!r} not supported on the GPU path (average, min, max)")
+    if ties_method not in L.TIES or ties_method == "dense":  # base::rank has no "dense"; "random" draws from R's RNG
+        raise ValueError(f"ties.method {ties_method!r} not supported (average, min, max, first, last)")
     m = sp.csc_matrix(X).astype(np.float64)
     m.sort_indices()
     keep: list = []
@@ -378,7 +378,7 @@ def colranks(X, sparse: Optional[bool] = None, signed: bool = False, keep_zero: 
     (R/plaid.R:589-623).  csc_matrix for (sparse & keep_zero), else a dense P x N array."""
     ctx = ctx or default_context()
     if ties_method not in L.TIES:
-        raise ValueError(f"ties.method {ties_method!r} not supported on the GPU path (average, min, max)")
+        raise ValueError(f"ties.method {ties_method!r} not supported (average, min, max, first, last, dense)")
     is_sp = sp is not None and sp.issparse(X)
     if sparse is None:
         sparse = is_sp

@@ -2336,7 +2336,10 @@ int plaidgpu_colranks(plaidgpu_ctx* c, const plaidgpu_matrix* X, int ties, int i
                       int out_location, double* out) try {
   if (!c) return PLAIDGPU_ERR_ARG;
   if (!X || !out) return fail(c, PLAIDGPU_ERR_ARG, "null argument");
-  if (ties < PLAIDGPU_TIES_AVERAGE || ties > PLAIDGPU_TIES_MAX) return fail(c, PLAIDGPU_ERR_ARG, "unsupported ties.method");
+  if (ties < PLAIDGPU_TIES_AVERAGE || ties > PLAIDGPU_TIES_DENSE) return fail(c, PLAIDGPU_ERR_ARG, "unsupported ties.method");
+  if (ties > PLAIDGPU_TIES_MAX && X->kind == PLAIDGPU_CSC && !keep_zero)
+    return fail(c, PLAIDGPU_ERR_ARG, "ties.method first / last / dense: not available for sparse input without keep.zero "
+                                     "(sparseMatrixStats::colRanks knows max, average, min)");
   trace("begin");
   CK(cudaSetDevice(c->device));
   c->in_call = false;

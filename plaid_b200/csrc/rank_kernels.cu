@@ -24,10 +24,11 @@ constexpr int RT_MAX = 1024;  // long columns (one CTA per SM by shared memory):
 constexpr unsigned long long ZERO_KEY = 0x8000000000000000ull;
 constexpr unsigned long long NAN_KEY = ~0ull;
 
+// stable: equal keys are ordered by position (ties.method first / last / dense need the order of appearance)
 template <typename PosT>
-__device__ __forceinline__ void cas(unsigned long long* k, PosT* p, int i, int l) {
+__device__ __forceinline__ void cas(unsigned long long* k, PosT* p, int i, int l, bool stable) {
   const unsigned long long a = k[i], b = k[l];
-  if (a > b) {
+  if (a > b || (stable && a == b && p[i] > p[l])) {
     k[i] = b;
     k[l] = a;
     const PosT t = p[i];
@@ -37,7 +38,7 @@ __device__ __forceinline__ void cas(unsigned long long* k, PosT* p, int i, int l
 }
 
 template <typename PosT>
-__device__ void bitonic_sort(unsigned long long* k, PosT* p, int n) {
+__device__ void bitonic_sort(unsigned long long* k, PosT* p, int n, bool stable = false) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const int half = np2 >> 1;
@@ -46,13 +47,13 @@ __device__ void bitonic_sort(unsigned long long* k, PosT* p, int n) {
     for (int q = threadIdx.x; q < half; q += blockDim.x) {  // flip step
       const int blk = q / hs, o = q - blk * hs;
       const int i = blk * size + o, l = blk * size + size - 1 - o;
-      if (l < n) cas(k, p, i, l);
+      if (l < n) cas(k, p, i, l, stable);
     }
     __syncthreads();
     for (int stride = size >> 2; stride >= 1; stride >>= 1) {
       for (int q = threadIdx.x; q < half; q += blockDim.x) {
         const int i = 2 * stride * (q / stride) + (q % stride), l = i + stride;
-        if (l < n) cas(k, p, i, l);
+        if (l < n) cas(k, p, i, l, stable);
       }
       __syncthreads();
     }
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankPar
     bool fast_done = false;
     double mymax = 0.0;
     int nneg_f = 0, z_f = 0;
-    if (!GLOBAL_WS) {
+    const bool ordered = p.ties > PLAIDGPU_TIES_MAX;  // first / last / dense: stable network, order of appearance
+    if (!GLOBAL_WS && !ordered) {
       for (int i = tid; i < RANK_HT; i += RT) {
         sf.tab[i] = NAN_KEY;  // empty (NaN entries never enter the table)
         sf.cnt[i] = 0u;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankPar
     if (my_nan) atomicAdd(&s_nnan, my_nan);
     __syncthreads();
     bool bucket_done = false;
-    if (!GLOBAL_WS && p.ss_max >= 32 && n >= BUCKET_MIN_N) {
+    if (!GLOBAL_WS && !ordered && p.ss_max >= 32 && n >= BUCKET_MIN_N) {
       // ---- bucket path: splitters from a sorted sample, counting, direct ranking inside the interval buckets ----
       int SS = 32;
       // keys per interval bucket: 8-16 where the CTA owns the SM anyway, 32-64 for short columns (a larger bucket
@@ -479,8 +481,47 @@ __global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankPar
       __syncthreads();
     }
     if (!bucket_done) {
-    bitonic_sort<PosT>(keys, pos, n);
+    bitonic_sort<PosT>(keys, pos, n, ordered);
     const int nv = n - s_nnan;  // NaN sorted last
+    if (p.ties == PLAIDGPU_TIES_DENSE) {
+      // RT partial sums: the (idle) bucket region behind keys + positions; global workspace variant: the dynamic buffer
+      unsigned* const s_part = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(rsm) + (GLOBAL_WS ? 0 : p.bucket_off));
+      // rank = number of distinct values <= the key: run starts counted per contiguous chunk of sorted slots, scanned
+      const int per = (nv + RT - 1) / RT, a = min(nv, tid * per), b = min(nv, a + per);
+      unsigned cntd = 0;
+      for (int q = a; q < b; ++q) cntd += (q == 0 || keys[q] != keys[q - 1]);
+      s_part[tid] = cntd;
+      __syncthreads();
+      if (tid < 32) {
+        unsigned loc = 0;
+        for (int i = 0; i < RT / 32; ++i) loc += s_part[tid * (RT / 32) + i];
+        unsigned incl = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(FULL, incl, o);
+          if (tid >= o) incl += t;
+        }
+        unsigned run = incl - loc;
+        for (int i = 0; i < RT / 32; ++i) {
+          const unsigned t = s_part[tid * (RT / 32) + i];
+          s_part[tid * (RT / 32) + i] = run;
+          run += t;
+        }
+      }
+      __syncthreads();
+      unsigned d = s_part[tid];
+      for (int q = a; q < b; ++q) {
+        d += (q == 0 || keys[q] != keys[q - 1]);
+        double r = (double)d;
+        if (p.is_signed) {
+          const double v = p.xx[c0 + pos[q]];
+          r = v > 0.0 ? r : (v < 0.0 ? -r : 0.0);
+        }
+        mymax = fmax(mymax, fabs(r));
+        p.rank[c0 + pos[q]] = r;
+      }
+      for (int q = nv + tid; q < n; q += RT) p.rank[c0 + pos[q]] = nan("");
+    } else {
     // zero group (dense semantics): stored zeros + implicit zeros
     int zs = 0, zimp = 0;
     nneg = 0;
@@ -510,7 +551,9 @@ __global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankPar
         }
         r = p.ties == PLAIDGPU_TIES_AVERAGE ? 0.5 * (double)(first + 1 + last)
             : p.ties == PLAIDGPU_TIES_MIN   ? (double)(first + 1)
-                                            : (double)last;
+            : p.ties == PLAIDGPU_TIES_MAX   ? (double)last
+            : p.ties == PLAIDGPU_TIES_FIRST ? (double)(q + 1)            // the stable order IS the order of appearance
+                                            : (double)(first + last - q);  // last: the run in reverse
         if (p.is_signed) {
           const double v = p.xx[c0 + pos[q]];
           r = v > 0.0 ? r : (v < 0.0 ? -r : 0.0);
@@ -519,6 +562,7 @@ __global__ void __launch_bounds__(WIDE ? RT_MAX : RT_SHORT) k_rank(const RankPar
       }
       p.rank[c0 + pos[q]] = r;
     }
+    }  // ties != dense
     }  // !bucket_done
     }  // !fast_done
     double rz = 0.0;
@@ -650,7 +694,7 @@ cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_
   }
   p.ss_max = ss;
   p.bucket_off = need;
-  if (ss) need += bucket_bytes(ss);
+  need += ss ? bucket_bytes(ss) : (size_t)threads * 4;  // at least the partial sums of the dense-rank scan
   if (need < sizeof(RankFast<1024>)) need = sizeof(RankFast<1024>);
   if (wide && need < sizeof(RankFast<2048>)) need = sizeof(RankFast<2048>);
   cudaError_t e;
@@ -680,7 +724,7 @@ cudaError_t launch_rank_impl(RankParams p, int max_n, int64_t total, cudaStream_
   p.ws_pos = wp;
   int64_t grid = (int64_t)sm_count() * 4;
   if (grid > p.N) grid = p.N;
-  k_rank<PosT, true, false><<<(unsigned)grid, RT_SHORT, 0, st>>>(p);
+  k_rank<PosT, true, false><<<(unsigned)grid, RT_SHORT, RT_SHORT * sizeof(unsigned), st>>>(p);
   e = cudaGetLastError();
   cudaFreeAsync(wk, st);
   cudaFreeAsync(wp, st);

@@ -87,9 +87,11 @@ sparse_colranks <- function(X, signed = FALSE, ties.method = "average") {   # R/
   rX
 }
 
+## ties.method -> PLAIDGPU_TIES_*: "first" / "last" (base::rank, matrixStats) and "dense" (matrixStats) are ranked in
+## order of appearance on the device; "random" draws from R's RNG and is not available
 .ties <- function(m) {
-  k <- match(m, c("average", "min", "max"))
-  if (is.na(k)) stop("ties.method '", m, "' is not available on the GPU path (average, min, max)")
+  k <- match(m, c("average", "min", "max", "first", "last", "dense"))
+  if (is.na(k)) stop("ties.method '", m, "' is not available on the GPU path (average, min, max, first, last, dense)")
   k - 1L
 }
 

@@ -289,6 +289,45 @@ def test_colranks_counting_and_sorting_paths_agree(gpu_ctx):
     same(pb.colranks(D, ctx=gpu_ctx), O.colranks(D))
 
 
+def test_colranks_order_of_appearance_ties(gpu_ctx):
+    """ties.method first / last (base::rank via sparse_colranks, matrixStats::colRanks on dense input) and dense
+    (matrixStats only): bit-exact vs the oracle incl. signed ranks, NaN, -0, short and long columns; the methods R does
+    not offer on a branch are errors here too"""
+    rng = np.random.default_rng(44)
+    P = 3000
+    D = np.round(rng.normal(size=(P, 6)), 1)          # heavy ties
+    D[:, 1] = rng.normal(size=P)                       # all distinct
+    D[::50, 2] = np.nan
+    D[:, 3] = np.where(rng.random(P) < 0.5, 0.0, -0.0)
+    D[:, 4] = 7.0
+    Dl = np.round(rng.normal(size=(20000, 2)), 2)      # bulk-sized columns
+
+    def same(a, b):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+    for ties in ("first", "last", "dense"):
+        for signed in (False, True):
+            same(pb.colranks(D, signed=signed, ties_method=ties, ctx=gpu_ctx), O.colranks(D, signed=signed, ties_method=ties))
+        same(pb.colranks(Dl, ties_method=ties, ctx=gpu_ctx), O.colranks(Dl, ties_method=ties))
+    X = synth.sparse_x_numpy(2000, 30, seed=45, density=0.2)
+    X.data[::7] *= -1.0
+    X.data[::11] = 0.0
+    for ties in ("first", "last"):
+        for signed in (False, True):
+            same(pb.sparse_colranks(X, signed=signed, ties_method=ties, ctx=gpu_ctx).data,
+                 O.sparse_colranks(X, signed=signed, ties_method=ties).data)
+            same(pb.colranks(X, keep_zero=True, signed=signed, ties_method=ties, ctx=gpu_ctx).data,
+                 O.sparse_colranks(X, signed=signed, ties_method=ties).data)
+    with pytest.raises(ValueError):
+        pb.sparse_colranks(X, ties_method="dense", ctx=gpu_ctx)      # base::rank has no "dense"
+    with pytest.raises(ValueError):
+        pb.colranks(X, ties_method="random", ctx=gpu_ctx)            # R's RNG
+    from plaid_b200 import _lib as L
+    with pytest.raises(L.PlaidGpuError):
+        pb.colranks(X, ties_method="first", ctx=gpu_ctx)             # sparseMatrixStats::colRanks: max / average / min
+
+
 def test_colranks_bucket_path_many_distinct_values(gpu_ctx):
     """columns with many distinct values are ranked by the splitter / bucket path of k_rank (no sort): dense bulk
     columns of 20,000 distinct values, mixtures of large tie classes and distinct values, signed ranks, dense

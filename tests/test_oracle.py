@@ -33,6 +33,23 @@ def test_rank_vector_vs_scipy(ties):
         assert np.array_equal(O.rank_vector(v, ties), rankdata(v, method=ties))
 
 
+def test_rank_vector_order_of_appearance_methods():
+    """ties.method first / last (base::rank) and dense (matrixStats::colRanks), R's documented example first:
+    rank(c(3, 1, 4, 1, 5, 9, 2, 6, 5, 3, 5)) from ?rank"""
+    x = np.array([3, 1, 4, 1, 5, 9, 2, 6, 5, 3, 5], dtype=float)
+    assert np.array_equal(O.rank_vector(x, "first"), [4, 1, 6, 2, 7, 11, 3, 10, 8, 5, 9])   # ?rank: rank(x2, ties = "first")
+    assert np.array_equal(O.rank_vector(x, "last"), [5, 2, 6, 1, 9, 11, 3, 10, 8, 4, 7])
+    assert np.array_equal(O.rank_vector(x, "dense"), [3, 1, 4, 1, 5, 7, 2, 6, 5, 3, 5])
+    rng = np.random.default_rng(2)
+    for n in [1, 2, 9, 500]:
+        v = rng.integers(-4, 5, size=n).astype(float) * 0.5
+        v[rng.random(n) < 0.1] = -0.0
+        assert np.array_equal(O.rank_vector(v, "first"), rankdata(v, method="ordinal"))
+        assert np.array_equal(O.rank_vector(v, "dense"), rankdata(v, method="dense"))
+        # last = first of the reversed vector, reversed back
+        assert np.array_equal(O.rank_vector(v, "last"), rankdata(v[::-1], method="ordinal")[::-1])
+
+
 def test_rank_vector_nan_kept():
     v = np.array([3.0, np.nan, 1.0, 3.0])
     r = O.rank_vector(v, "average")
