@@ -1486,6 +1486,7 @@ int plaidgpu_score_compute(plaidgpu_ctx* c, plaidgpu_scalars* scal, double* out)
       t.tail = tail ? c->b_ttmp.as<long long>() : nullptr;
       t.tail_ld = (int64_t)tiles * TC_;
       t.colfb = (tail && p.mode >= XF_SING) ? c->b_colfb.as<double>() + j0 : nullptr;
+      t.small_sums = c->P <= (1 << 20) ? 1 : 0;
       CK(launch_tc_score(t, c->b_tcB.as<signed char>(), c->tcK, sl, c->stream));
       c->launches += 2;
       if (c->early_out && t.final && j0 + nj <= early_limit) {
@@ -1873,7 +1874,7 @@ int plaidgpu_score_finish(plaidgpu_ctx* c, const plaidgpu_scalars* scal, double*
 // `sink` (optional): instead of landing in `out`, every finished chunk is staged in a pinned buffer and
 // written to the file — tiled egress for results larger than host memory (scope row f4).
 static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_t* rowmap, const plaidgpu_opts* opts,
-                         double* out, int64_t chunk, FILE* sink = nullptr, double* stage = nullptr) {
+                         double* out, int64_t chunk, FILE* sink = nullptr, double* stage = nullptr, double* stage2 = nullptr) {
   const int64_t N = X->N;
   const int32_t S = c->S;
   if (opts->scorer == PLAIDGPU_GSVA && opts->gsva_ecdf != PLAIDGPU_ROWTF_DONE &&
@@ -1943,7 +1944,17 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
   }
   plaidgpu_opts o2 = *opts;
   if (norm) o2.ignore_zero = g.ignore_zero;  // decided: the second pass needs only that median
-  for (int64_t j0 = 0; j0 < N; j0 += chunk) {
+  // file sink: tile k is written by a helper thread from one staging buffer while tile k + 1 is scored into the other
+  std::thread writer;
+  bool short_write = false;
+  struct WriterJoin {
+    std::thread& t;
+    ~WriterJoin() {
+      if (t.joinable()) t.join();
+    }
+  } writer_join{writer};  // also on the error returns below
+  int64_t tile = 0;
+  for (int64_t j0 = 0; j0 < N; j0 += chunk, ++tile) {
     const int64_t j1 = std::min(N, j0 + chunk);
     sub(j0, j1, &M);
     rc = plaidgpu_score_begin(c, &M, rowmap, &o2, &loc);
@@ -1953,13 +1964,21 @@ static int score_chunked(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int32_
     if (rc) return rc;
     s.ignore_zero = g.ignore_zero;
     s.med_mean = g.med_mean;
-    rc = plaidgpu_score_finish(c, &s, sink ? stage : out + j0 * (int64_t)S);
+    double* dst = sink ? ((stage2 && (tile & 1)) ? stage2 : stage) : out + j0 * (int64_t)S;
+    if (sink && !stage2 && writer.joinable()) writer.join();  // one buffer only: it must be free again
+    rc = plaidgpu_score_finish(c, &s, dst);
     if (rc) return rc;
     if (sink) {
+      if (writer.joinable()) writer.join();  // tile k - 1 on disk (its buffer is the one tile k + 1 will use)
+      if (short_write) return fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
       const size_t cnt = (size_t)(j1 - j0) * (size_t)S;
-      if (fwrite(stage, sizeof(double), cnt, sink) != cnt) return fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
+      writer = std::thread([dst, cnt, sink, &short_write] {
+        if (fwrite(dst, sizeof(double), cnt, sink) != cnt) short_write = true;
+      });
     }
   }
+  if (writer.joinable()) writer.join();
+  if (short_write) return fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
   return PLAIDGPU_OK;
 }
 
@@ -1976,7 +1995,9 @@ int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int3
   // column tile: what the device can hold next to X and the ranks, capped at 1 GiB of pinned staging
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
+  // (two staging buffers of half that when the result takes several tiles: tile k is written while k + 1 is scored)
   double budget = std::min(0.45 * (double)free_b + (double)c->b_raw.cap, (double)(1ull << 30));
+  if ((double)S * 8.0 * (double)N > budget) budget *= 0.5;
   if (const char* e = getenv("PLAIDGPU_MAX_OUT_BYTES")) budget = atof(e);  // test knob
   int64_t chunk = (int64_t)(budget / ((double)S * 8.0));
   if (chunk < 1) chunk = 1;
@@ -1995,7 +2016,9 @@ int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int3
     fwrite(dict.data(), 1, dict.size(), f);
   }
   double* stage = nullptr;
-  cudaError_t e = cudaMallocHost(&stage, std::max<size_t>((size_t)chunk * (size_t)S * sizeof(double), 8));
+  const size_t stage_elems = std::max<size_t>((size_t)chunk * (size_t)S, 1);
+  const bool tiled = N > chunk;
+  cudaError_t e = cudaMallocHost(&stage, stage_elems * sizeof(double) * (tiled ? 2 : 1));
   if (e != cudaSuccess) {
     fclose(f);
     return fail_cuda(c, e, "cudaMallocHost (file staging)");
@@ -2008,7 +2031,7 @@ int plaidgpu_score_to_file(plaidgpu_ctx* c, const plaidgpu_matrix* X, const int3
     const size_t cnt = (size_t)N * (size_t)S;
     if (!rc && cnt && fwrite(stage, sizeof(double), cnt, f) != cnt) rc = fail(c, PLAIDGPU_ERR_ARG, "short write to the output file");
   } else {
-    rc = score_chunked(c, X, rowmap, &o, nullptr, chunk, f, stage);
+    rc = score_chunked(c, X, rowmap, &o, nullptr, chunk, f, stage, stage + stage_elems);
   }
   cudaFreeHost(stage);
   if (fclose(f) != 0 && !rc) rc = fail(c, PLAIDGPU_ERR_ARG, "closing the output file failed");

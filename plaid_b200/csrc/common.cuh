@@ -116,6 +116,8 @@ struct TcParams {
   int64_t tail_ld;
   const double* colfb;   // [N] f(rank of the zero group) per column (rank scorers on sparse X), or nullptr
   int32_t dbg;           // development switches (PLAIDGPU_TC_DBG): 1 no tail loads, 2 no wait for A, 4 no wait for B
+  int32_t small_sums;    // every integer set sum is below 2^51 in magnitude (rows <= 2^20, |q| < 2^30): the fast epilogue's
+                         // int64 -> fp64 conversion is an integer add + one DADD instead of I2F.F64.S64
 };
 
 struct LaunchCfg {

@@ -179,7 +179,10 @@ __device__ __forceinline__ void tc_epi_fast(const uint32_t (&v)[32], uint32_t tr
     const int lo = (int)v[4 * c] + ((int)v[4 * c + 1] << 8);
     const int hi = (int)v[4 * c + 2] + ((int)v[4 * c + 3] << 8);
     const long long tot = (long long)hi * 65536ll + tl[c] + (long long)lo;
-    double x = (double)tot;
+    // exact int64 -> fp64 for |tot| < 2^51 (the fast path's precondition, TcParams::small_sums): tot added to the bit
+    // pattern of 2^52 + 2^51 is that double plus tot ulps of 1; one DADD takes the bias off again.  I2F.F64.S64 is a
+    // multi-pass instruction on the narrow fp64 pipe, which the 8 epilogue warps saturate (stall_math)
+    double x = __longlong_as_double(tot + 0x4338000000000000ll) - 6755399441055744.0;
     int xh = __double2hiint(x);
     xh = tot != 0 ? xh + ed[c] : xh;  // x * 2^-e_j (prep keeps e_j far from the exponent limits)
     x = __hiloint2double(xh, __double2loint(x));
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_score(const __grid_constan
     double vmin = INFINITY;
     uint32_t negbits = 0;   // fast path: OR of the high words of the scores (sign bit = some score is negative)
     bool anyzero = false;   //            some score is exactly zero
-    const bool fastable = SLICES == 4 && p.final && rows_full && (!rankmode || p.colfb != nullptr) && !(p.dbg & 32);
+    const bool fastable = SLICES == 4 && p.final && rows_full && (!rankmode || p.colfb != nullptr) && !(p.dbg & 32) && p.small_sums;
     constexpr int CPC = 32 / SLICES;  // cells per 32-column chunk
     const uint32_t tsw = (uint32_t)(lane & 7);
     // high words of 2^-e_j for the chunk this warp handles next (fast path): fetched one chunk ahead, so the L2
