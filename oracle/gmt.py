@@ -20,7 +20,13 @@ def read_gmt(path: str) -> "list[tuple[str, list[str]]]":
     with open(path, "r", encoding="utf-8", errors="replace") as fh:
         for line in fh:
             line = line.rstrip("\r\n")
-            if not line or line.startswith("#"):
+            # utils::read.csv(sep = "!", comment.char = "#")[, 1]  (:108): '#' ends the line wherever it stands and only
+            # the text before the first '!' (the separator) is kept; empty lines are skipped (quote handling not restated)
+            for ch in "#!":
+                k = line.find(ch)
+                if k >= 0:
+                    line = line[:k]
+            if not line:
                 continue
             f = line.split("\t")
             name = f[0]

@@ -35,7 +35,15 @@ void parse(const char* text, size_t len, std::vector<RawSet>& sets) {
     while (eol < len && text[eol] != '\n') ++eol;
     size_t end = eol;
     if (end > pos && text[end - 1] == '\r') --end;
-    if (end > pos && text[pos] != '#') {  // comment.char = "#" (:108)
+    // utils::read.csv(sep = "!", comment.char = "#")[, 1]  (:108): '#' ends the line wherever it stands, '!' is the
+    // column separator (only the first column is kept) and a line that is empty afterwards is skipped.  Deviation
+    // kept: read.csv's quote = "\"" (a double quote would start a field in which '!', '#' and line ends are literal)
+    for (size_t i = pos; i < end; ++i)
+      if (text[i] == '#' || text[i] == '!') {
+        end = i;
+        break;
+      }
+    if (end > pos) {
       RawSet s;
       int field = 0;
       size_t f0 = pos;

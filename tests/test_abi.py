@@ -92,10 +92,12 @@ def test_gmt_ingestion_matches_oracle(tmp_path):
     assert got.colnames == cn and got.rownames == rn
     assert (got.mat != D).nnz == 0
     tricky = tmp_path / "t.gmt"
-    tricky.write_bytes(b"# comment\nS1\tsrc\tA\tB\tNA\tB\t\tC D\r\nS2\tsrc\tB\nS1\tdup\tZ\tY\tX\tW\tV\tU\nS3\tsrc\n")
+    tricky.write_bytes(b"# comment\nS1\tsrc\tA\tB\tNA\tB\t\tC D\r\nS2\tsrc\tB\nS1\tdup\tZ\tY\tX\tW\tV\tU\nS3\tsrc\n"
+                       b"S4\tsrc\tA\tQ # trailing comment\tNOTAGENE\nS5\tsrc\tB\tR!second column\tNOTAGENE\n#\n!x\n")
     got = gmt2mat_file(str(tricky))
     D, rn, cn = gmt2mat(read_gmt(str(tricky)))
     assert got.colnames == cn and got.rownames == rn and (got.mat != D).nnz == 0
+    assert "NOTAGENE" not in got.rownames and "Q" in got.rownames and "R" in got.rownames  # '#' / '!' cut the line (read.csv)
     # rowmap: first occurrence of a duplicated X rowname wins, unknown names -> -1
     lib = L.load()
     h = C.c_void_p()
