@@ -18,7 +18,8 @@ normalisation) over the rank's shard.
   cpu_baseline  the oracle (numpy/scipy restatement of the R path) on 1 host core, bounded sample.
 
 Other workloads (same JSON line, same keys): "ssgsea" / "ucell" = replaid.ssgsea(alpha=0) / replaid.ucell on the
-same sparse shard (BASELINE.json configs[2] / configs[4], the north star's second target), "plaid_dense" =
+same sparse shard (BASELINE.json configs[2] / configs[4], the north star's second target), "sing" / "aucell" = the
+other two rank scorers SURVEY section 8(d) names for C3 / C5, "plaid_dense" =
 plaid() on a dense 20,000 x 1,000 bulk matrix (configs[1]; N GPUs run N replicas).
 """
 from __future__ import annotations
@@ -49,7 +50,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
-    ap.add_argument("--workload", default="plaid", choices=["plaid", "ssgsea", "ucell", "plaid_dense"])
+    ap.add_argument("--workload", default="plaid", choices=["plaid", "ssgsea", "ucell", "plaid_dense", "sing", "aucell"])
     ap.add_argument("--e2e-cells", type=int, default=-1,
                     help="cells per GPU of the host-buffer e2e legs (-1 = the full shard when host memory allows, 0 = skip)")
     ap.add_argument("--cpu-cells", type=int, default=3000, help="cells of the 1-core CPU baseline sample (0 = skip)")
@@ -128,7 +129,12 @@ WORKLOADS = {
     "ucell": ("UCELL", dict(rmax=1500.0), "replaid.ucell(rmax=1500): dense-semantics column ranks + product + normalisation",
               "configs[4] (C5) as its per-GPU shard"),
     "plaid_dense": ("PLAID", dict(stats_mean=1, normalize=1), "plaid() on a dense bulk matrix: stats=mean, normalize=TRUE", "configs[1] (C2)"),
+    "sing": ("SING", dict(nrow_x=P_GENES), "replaid.sing(): dense-semantics column ranks (ties = min), r / nrow(X) - 0.5, product (no normalisation)",
+             "configs[2] (C3), on the C4 shard"),
+    "aucell": ("AUCELL", dict(auc_max_rank=1000.0), "replaid.aucell(aucMaxRank=1000): dense-semantics column ranks + product + normalisation",
+               "configs[4] (C5) as its per-GPU shard"),
 }
+RANK_WORKLOADS = ("ssgsea", "ucell", "sing", "aucell")
 DENSE_N = 1000
 
 
@@ -271,7 +277,7 @@ def run_ours(a):
     else:
         alg_bytes = nnz * 12 + (Nc + 1) * 4 + nnzG * 4 + (S_SETS + 1) * 4 + S_SETS * Nc * 8
         alg_formula = "nnzX*12 + (N+1)*4 + nnzG*4 + (S+1)*4 + S*N*8"
-        if wl in ("ssgsea", "ucell"):
+        if wl in RANK_WORKLOADS:
             alg_bytes += nnz * 8  # fused rank scorers: the ranks are read once more (B_plaid + nnzX*8)
             alg_formula += " + nnzX*8 (ranks)"
     score_ms = score_ms_sum / a.steps
@@ -406,7 +412,8 @@ def run_ours(a):
 
 def _oracle_fn(wl):
     from oracle import plaid_oracle as O
-    return {"plaid": O.plaid, "plaid_dense": O.plaid, "ssgsea": O.replaid_ssgsea, "ucell": O.replaid_ucell}[wl]
+    return {"plaid": O.plaid, "plaid_dense": O.plaid, "ssgsea": O.replaid_ssgsea, "ucell": O.replaid_ucell,
+            "sing": O.replaid_sing, "aucell": lambda X, G: O.replaid_aucell(X, G, aucMaxRank=1000)}[wl]
 
 
 def cpu_baseline_dense(G, Xh, names, wl):
