@@ -363,6 +363,31 @@ def run_ours(a):
                "note": "host buffers pinned; the same call incl. normalisation; H2D of X and D2H of the S x N result inside the timed "
                        "region (chunks of raw scores leave while later chunks are scored); pcie_floor_ms = d2h bytes / the box's measured "
                        "concurrent D2H rate"}
+        # score -> test: plaid() fused with the group sums of plaid.test(tests = "lm") — the same host X goes
+        # up, 4 * S doubles come back, the S x N matrix never crosses PCIe (one context: N = 1 only)
+        if wl == "plaid" and world == 1:
+            try:
+                yv = (np.arange(Ne) % 2).astype(np.int32)
+                mo = np.empty(4 * S_SETS, dtype=np.float64)
+
+                def fstep():
+                    ctx.check(lib.plaidgpu_score_group_moments(ctx.h, C.byref(Mh), rowmap.ctypes.data, C.byref(oh), yv.ctypes.data,
+                                                               mo.ctypes.data))
+                fstep()
+                torch.cuda.synchronize()
+                kf = max(1, min(a.steps, 5))
+                t0 = time.perf_counter()
+                for _ in range(kf):
+                    fstep()
+                    _ = float(mo[0]) + float(mo[-1])
+                torch.cuda.synchronize()
+                fsec = (time.perf_counter() - t0) / kf
+                e2e["fused_test"] = {"value": S_SETS * float(Ne) / fsec, "unit": UNIT, "ms_per_step": round(fsec * 1e3, 2), "steps": kf,
+                                     "h2d_bytes_per_step": int(h2d) + Ne * 4, "d2h_bytes_per_step": 4 * S_SETS * 8,
+                                     "note": "plaidgpu_score_group_moments: plaid() + the per-set group sums / sums of squares of "
+                                             "plaid.test(tests='lm') as one call; scores stay on the device, normalisation applied in registers"}
+            except Exception as ex:  # the headline legs above stand on their own
+                e2e["fused_test"] = {"error": str(ex)[:200]}
         # what an R caller gets: pageable (malloc) buffers on both sides, the library's pinned ring + copy threads
         try:
             pout = np.empty(S_SETS * Ne, dtype=np.float64)
