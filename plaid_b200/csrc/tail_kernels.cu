@@ -116,7 +116,11 @@ __global__ void __launch_bounds__(256) k_tile_place(const int32_t* __restrict__ 
         if (gg[u] < 0) continue;
         double v = xform_value(mode, xv[u], a0, a1);
         if (mode >= XF_SING) v -= fb;
-        ent[pos[u]] = make_uint2((uint32_t)(int32_t)__double2ll_rn(v * sc), cell);
+        const int32_t q = (int32_t)__double2ll_rn(v * sc);
+        // a non-zero tail entry that the column's fixed point would flush to zero: the call is redone in fp64
+        // (tc_kernels.cu, k_tc_prep_dense); every kernel after this one looks at the flag before it starts
+        if (q == 0 && v != 0.0 && skip_if) atomicExch(const_cast<int*>(skip_if), 1);
+        ent[pos[u]] = make_uint2((uint32_t)q, cell);
       }
     }
   }

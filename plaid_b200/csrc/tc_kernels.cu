@@ -644,6 +644,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_csc(const int32_t* __restrict__
           double v = xform_value(mode, x, a0, a1);
           if (mode >= XF_SING) v -= fb;
           const long long q = (fabs(v) <= 1.0e300) ? __double2ll_rn(v * sc) : 0ll;
+          if (q == 0 && v != 0.0) atomicExch(flag, 1);  // would become an exact zero (see k_tc_prep_dense): fp64 passes instead
           signed char dg[SLICES];
           digits_of<SLICES>(q, dg);
 #pragma unroll
@@ -707,6 +708,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_dense(const double* __restrict_
     const double sc = ldexp(1.0, ex);
     if (tid == 0) colinv[j] = ldexp(1.0, -ex);
     signed char* __restrict__ rows = Bd + (size_t)j * SLICES * Kp;
+    bool lost = false;
     // 16 consecutive genes per thread: one 16-byte store per digit row
     for (int g0 = tid * 16; g0 < Kp; g0 += 256 * 16) {
       signed char dg[SLICES][16];
@@ -717,6 +719,9 @@ __global__ void __launch_bounds__(256) k_tc_prep_dense(const double* __restrict_
         if (r < P) {
           const double v = xform_value(mode, col[r], a0, a1);
           q = (fabs(v) <= 1.0e300) ? __double2ll_rn(v * sc) : 0ll;
+          // a non-zero entry more than 2^31 below the column's largest would become an exact zero: zeros carry meaning
+          // on this path (normalize_medians drops them, R/plaid.R:557-566), so such a column takes the fp64 passes
+          if (q == 0 && v != 0.0) lost = true;
         }
         signed char d1[SLICES];
         digits_of<SLICES>(q, d1);
@@ -726,6 +731,7 @@ __global__ void __launch_bounds__(256) k_tc_prep_dense(const double* __restrict_
 #pragma unroll
       for (int k = 0; k < SLICES; ++k) *reinterpret_cast<uint4*>(rows + (size_t)k * Kp + g0) = *reinterpret_cast<const uint4*>(dg[k]);
     }
+    if (lost) atomicExch(flag, 1);
     __syncthreads();
   }
 }

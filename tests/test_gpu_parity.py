@@ -216,6 +216,26 @@ def test_gsva_z(fixture_mats, golden, gpu_ctx):
     assert rel_err(pb.replaid_gsva(Xg, Gg, rowtf="ecdf", ctx=gpu_ctx).mat, O.replaid_gsva(Xo, Go, rowtf="ecdf").mat) < tol(1e-9)
 
 
+def test_wide_dynamic_range_columns_keep_their_zero_pattern(gpu_ctx):
+    """a column whose entries span more than 2^31 cannot be held in the 30-bit per-column fixed point: its smallest
+    entries would become exact zeros, and zeros carry meaning (normalize_medians drops them, R/plaid.R:557-566) — the
+    library must notice and score the call in fp64 (found by tools/fuzz_paths.py: 1.5e-3 off without the guard)"""
+    rng = np.random.default_rng(35)
+    P, N, S = 3000, 49, 1500
+    X = sp.random(P, N, density=0.01, format="csc", random_state=3, data_rvs=lambda n: rng.lognormal(0.5, 0.8, n))
+    X.data *= 10.0 ** rng.integers(-6, 7, size=X.data.size)
+    G = synth.genesets_numpy(P, S, seed=36, size_cap=(3, 700))
+    names = synth.gene_names(P)
+    Xg, Gg, Xo, Go = _named(X, names, None, G, names, None)
+    want = O.plaid(Xo, Go).mat
+    got = pb.plaid(Xg, Gg, ctx=gpu_ctx).mat
+    assert rel_err(got, want) < tol(TOL)
+    raw_w, raw_g = O.plaid(Xo, Go, normalize=False).mat, pb.plaid(Xg, Gg, normalize=False, ctx=gpu_ctx).mat
+    assert np.array_equal(raw_g == 0, raw_w == 0)          # the zero pattern of the scores is the reference's
+    D = X.toarray()                                         # the same through the dense-input path
+    assert rel_err(pb.plaid(pb.NamedMatrix(D, names), Gg, ctx=gpu_ctx).mat, O.plaid(O.Named(D, names), Go).mat) < tol(TOL)
+
+
 # ---- ranking: bit-exact, adversarial -----------------------------------------------------------
 @pytest.mark.parametrize("ties", ["average", "min", "max"])
 @pytest.mark.parametrize("signed", [False, True])
