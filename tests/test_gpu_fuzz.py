@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tool,seed,cases", [("fuzz_oracle.py", 101, 60), ("fuzz_paths.py", 102, 12)])
+@pytest.mark.parametrize("tool,seed,cases", [("fuzz_oracle.py", 101, 60), ("fuzz_paths.py", 102, 12), ("fuzz_ranks.py", 103, 80)])
 def test_randomised_sweep(tool, seed, cases):
     env = dict(os.environ, SEED=str(seed), CASES=str(cases))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool)], env=env, capture_output=True, text=True, timeout=600)
