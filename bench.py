@@ -168,6 +168,33 @@ def pcie_floor(torch, dev, nbytes, world, dist):
     return n * reps / float(t[0]) / 1e9  # GB/s per GPU with `world` GPUs active
 
 
+def bind_to_gpu_node(torch, local):
+    """One process per GPU, bound to the CPUs of the GPU's own NUMA node (sysfs local_cpulist of its PCI function): the
+    pinned host buffers of the e2e leg — first touched by this process — and the library's copy threads then sit next
+    to the GPU's PCIe root instead of wherever the scheduler put the process.  Returns a short description for `config`."""
+    if os.environ.get("PLAID_BENCH_NO_NUMA_BIND"):
+        return "off"
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no local cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"cpus {spec} (node of {bdf})"
+    except Exception as ex:  # no sysfs / properties: run unbound
+        return f"unbound ({type(ex).__name__})"
+
+
 # ---------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch
@@ -182,6 +209,7 @@ def run_ours(a):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_node(torch, local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -427,7 +455,7 @@ def run_ours(a):
                                   "inputs_exceed_l2 (X 2.1 GB + out 30 GB per GPU vs 126 MB L2; no flush needed)"),
                            "precision": "30-bit per-column fixed point on the tensor cores + integer tail sums (exact integer accumulation), "
                                         "fp64 epilogue: <= 2e-9 relative to the oracle at this shape (tests/test_gpu_parity.py); north star allows 1e-6",
-                           "timing": "K steps bracketed by barrier + cuda synchronize, max over ranks"},
+                           "numa_binding": numa, "timing": "K steps bracketed by barrier + cuda synchronize, max over ranks"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         _emit(line)
     if dist is not None:
