@@ -2,8 +2,13 @@
 
 TEST INFRASTRUCTURE — NOT PRODUCT CODE (see oracle/__init__.py).  PARITY: plaid() +
 normalize_medians are PINNED by the p-values the reference's vignette prints for its fixture
-(tests/test_reference_known_answers.py); the rank functions and replaid.* scorers are UNPINNED
-(the reference is R, cannot run here, and published no outputs for them).  Every function cites
+(tests/test_reference_known_answers.py, 7 digits); replaid.sing / replaid.ssgsea(alpha=0) /
+replaid.scse — and through them colranks(ties="min") with implicit zeros and
+sparse_colranks(ties="average") — are pinned TO PLOT RESOLUTION (about 1 % of a score's range) by
+the pairs() figure of the same vignette, the only output of the rank scorers the reference
+published (tests/test_reference_figure.py); replaid.ucell / .aucell / .gsva, colranks on dense
+input and the remaining ties methods are UNPINNED (the reference is R, cannot run here, and
+published no outputs for them).  Every function cites
 the reference lines it restates (paths relative to /root/reference) and is cross-checked by a
 second independent implementation in tests/test_oracle.py.
 
