@@ -6,8 +6,9 @@ Inputs: the reference's own bundled data (inst/extdata/pbmc3k-50cells.rda, hallm
 parsed without R by oracle/rdata.py + oracle/gmt.py.  Outputs: oracle/plaid_oracle.py results
 on them.  The reference itself (R) cannot run here, so these vectors pin the ORACLE; the oracle's
 plaid() + normalize_medians output is in turn pinned by the p-values the reference's vignette prints
-(extract_vignette.py, tests/test_reference_known_answers.py), the other functions are unpinned (see
-oracle/__init__.py).  The vectors let the GPU box — which has no /root/reference —
+(extract_vignette.py, tests/test_reference_known_answers.py), its replaid.sing / ssgsea / scse output to plot
+resolution by the vignette's pairs() figure (extract_vignette_figure.py, tests/test_reference_figure.py); the other
+functions are unpinned (see oracle/__init__.py).  The vectors let the GPU box — which has no /root/reference —
 test against the reference's real input.
 """
 import os
